@@ -1,0 +1,124 @@
+/*
+ * nastar_b200.h — C ABI of the B200-native differentiable-A* engine (libnastar_b200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference has no FFI: the
+ * seam is the Python attribute `self.astar = DifferentiableAstar(...)`
+ * (/root/reference/src/neural_astar/planner/astar.py:41-44,141-144) whose `.forward`
+ * (/root/reference/src/neural_astar/planner/differentiable_astar.py:150-267) is replaced.
+ * Each entry point below names the reference code it replaces.  All pointers are DEVICE
+ * pointers unless stated otherwise; no torch types cross this boundary.
+ *
+ * Plane layout: every "plane" argument is B maps of H*W contiguous fp32 cells (row-major,
+ * flat index = y*W + x, the same flat index the reference uses for `parents`,
+ * differentiable_astar.py:195-198).  `*_stride` is the distance between consecutive maps
+ * in ELEMENTS (so a [B,C,H,W] tensor's channel 0 is passed with stride C*H*W, matching
+ * `cost_maps[:, 0]`, differentiable_astar.py:177-180).
+ */
+#ifndef NASTAR_B200_H_
+#define NASTAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NASTAR_B200_ABI_VERSION 1
+
+/* status codes (the reference only has Python asserts, differentiable_astar.py:147,172-175) */
+enum {
+    NASTAR_OK = 0,
+    NASTAR_EINVAL = 1,      /* bad shape / null pointer / T < 1 */
+    NASTAR_EUNSUPPORTED = 2,/* map shape outside what this build handles */
+    NASTAR_ECUDA = 3,       /* a CUDA runtime call failed; see nastar_b200_last_cuda_error() */
+    NASTAR_EWORKSPACE = 4   /* workspace too small */
+};
+
+/* per-map outcome written to t_solve[] */
+#define NASTAR_TS_CAPPED (-1)    /* step cap T reached before the goal was selected */
+#define NASTAR_TS_EXHAUSTED (-2) /* open list ran empty: goal unreachable (the reference
+                                    produces NaN -> IndexError here) */
+
+typedef struct nastar_fwd_params {
+    /* inputs — differentiable_astar.py:150-157 (cost_maps, start_maps, goal_maps, obstacles_maps) */
+    const float *cost;   int64_t cost_stride;
+    const float *start;  int64_t start_stride;
+    const float *goal;   int64_t goal_stride;
+    const float *obst;   int64_t obst_stride;   /* may alias cost (VanillaAstar, astar.py:93-94) */
+    int32_t B, H, W;
+    /* scalars prepared on the host exactly as Python does (differentiable_astar.py:206):
+       g_ratio and (1 - g_ratio) evaluated in double, then rounded to fp32 */
+    float g_ratio;
+    float one_minus_g_ratio;
+    /* loop bound int(Tmax_eff * W * W), differentiable_astar.py:200-202 */
+    int32_t T;
+    /* outputs */
+    float   *histories;  /* [B][H*W] fp32 in {0,1}   — AstarOutput.histories, :265 */
+    int64_t *paths;      /* [B][H*W] int64 in {0,1}  — AstarOutput.paths (backtrack, :96-125) */
+    int32_t *t_solve;    /* [B] step at which the goal was selected, or NASTAR_TS_*; nullable */
+    int32_t *n_steps;    /* [B] number of selection steps executed for the map; nullable */
+    int32_t *trace;      /* [B][T] selected flat index per step (-1 beyond n_steps); nullable.
+                            Feeds store_intermediate_results (:210-216) */
+    /* scratch for maps whose state does not fit in shared memory; see
+       nastar_b200_forward_workspace_bytes().  nullable when that returns 0 */
+    void    *workspace;
+    size_t   workspace_bytes;
+} nastar_fwd_params;
+
+typedef struct nastar_bwd_params {
+    /* the forward's inputs again (the backward replays the deterministic search) */
+    const float *cost;   int64_t cost_stride;
+    const float *start;  int64_t start_stride;
+    const float *goal;   int64_t goal_stride;
+    const float *obst;   int64_t obst_stride;
+    int32_t B, H, W;
+    float g_ratio;
+    float one_minus_g_ratio;
+    float sqrt_w;             /* fl32(sqrt(W)), differentiable_astar.py:207 */
+    /* number of loop iterations the reference would have executed for this batch:
+       T_batch = min(T, 1 + max_b t_solve[b]) (batch-coupled stop, :251-252).  Read on the
+       DEVICE from *T_batch so that no host synchronisation is needed between forward
+       and backward */
+    const int32_t *T_batch;
+    const float *grad_histories; int64_t grad_stride; /* dL/d histories, [B][H*W] */
+    float *grad_cost;                                  /* dL/d cost_maps, [B][H*W], overwritten */
+    void  *workspace;
+    size_t workspace_bytes;
+} nastar_bwd_params;
+
+/* ABI version of the loaded library (== NASTAR_B200_ABI_VERSION at build time). */
+int nastar_b200_abi_version(void);
+
+/* Bytes of device scratch nastar_b200_forward needs for this shape (0 for maps that fit
+ * in shared memory, i.e. every BASELINE.json config up to 64x128). */
+size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W);
+size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W);
+
+/* Replaces DifferentiableAstar.forward's loop + backtrack (differentiable_astar.py:187-255).
+ * Asynchronous on `stream` (a cudaStream_t passed as void*). Returns NASTAR_*. */
+int nastar_b200_forward(const nastar_fwd_params *p, void *stream);
+
+/* Replaces autograd through the loop (closed form): writes dL/dcost. */
+int nastar_b200_backward(const nastar_bwd_params *p, void *stream);
+
+/* T_batch[0] = min(T, 1 + max_b n_steps-style stop) computed on the device from the forward's
+ * t_solve/n_steps arrays (replaces the host-synchronising torch.all(...) of :251). */
+int nastar_b200_batch_steps(const int32_t *t_solve, const int32_t *n_steps, int32_t B, int32_t T,
+                            int32_t *T_batch, void *stream);
+
+/* Which engine a shape dispatches to: 1 = warp-resident (H,W <= 32), 2 = generic warp engine
+ * with shared-memory state, 3 = generic with global-memory state, 0 = unsupported. */
+int nastar_b200_engine_for(int32_t H, int32_t W);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t nastar_b200_launch_count(void);
+
+const char *nastar_b200_status_string(int status);
+/* cudaGetErrorString of the last failing CUDA call made by this library (thread-unsafe, debug aid) */
+const char *nastar_b200_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NASTAR_B200_H_ */

@@ -1,0 +1,118 @@
+// nastar_api.cu — C-ABI entry points of libnastar_b200.so (see include/nastar_b200.h).
+// Host side only validates, picks an engine and launches; no torch types, no CPU fallback.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/nastar_b200.h"
+#include "nastar_fwd_warp32.cuh"
+
+namespace {
+std::atomic<uint64_t> g_launches{0};
+cudaError_t g_last_err = cudaSuccess;
+
+inline int cuda_fail(cudaError_t e) {
+    g_last_err = e;
+    return NASTAR_ECUDA;
+}
+
+__global__ void batch_steps_kernel(const int32_t* __restrict__ t_solve, const int32_t* __restrict__ n_steps,
+                                   int B, int T, int32_t* __restrict__ out) {
+    // T_batch = number of iterations of the reference's batch-synchronous loop
+    // (differentiable_astar.py:203,251-252): it stops right after the slowest map's solve step,
+    // or runs all T iterations if some map never reaches its goal.
+    int m = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const int ts = t_solve[i];
+        const int v = (ts >= 0) ? (ts + 1) : T;
+        m = max(m, v);
+        (void)n_steps;
+    }
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    __shared__ int sm[32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0;
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if (threadIdx.x == 0) out[0] = min(m, T);
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int nastar_b200_abi_version(void) { return NASTAR_B200_ABI_VERSION; }
+
+int nastar_b200_engine_for(int32_t H, int32_t W) {
+    if (H <= 0 || W <= 0) return 0;
+    if (H <= 32 && W <= 32) return 1;
+    return 0;
+}
+
+size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
+    (void)B; (void)H; (void)W;
+    return 0;
+}
+
+size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
+    (void)B; (void)H; (void)W;
+    return 0;
+}
+
+int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
+    if (!p || !p->cost || !p->start || !p->goal || !p->obst || !p->histories || !p->paths) return NASTAR_EINVAL;
+    if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->T < 1) return NASTAR_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int N = p->H * p->W;
+    const int engine = nastar_b200_engine_for(p->H, p->W);
+    if (engine == 0) return NASTAR_EUNSUPPORTED;
+    if (p->trace) {
+        cudaError_t e = cudaMemsetAsync(p->trace, 0xFF, size_t(p->B) * size_t(p->T) * sizeof(int32_t), stream);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
+    if (engine == 1) {
+        const size_t smem = nastar::Warp32Smem::bytes(N);
+        if (p->trace)
+            nastar::astar_fwd_warp32_kernel<true><<<p->B, 32, smem, stream>>>(*p);
+        else
+            nastar::astar_fwd_warp32_kernel<false><<<p->B, 32, smem, stream>>>(*p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
+}
+
+int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
+    (void)p; (void)stream_v;
+    return NASTAR_EUNSUPPORTED;
+}
+
+int nastar_b200_batch_steps(const int32_t* t_solve, const int32_t* n_steps, int32_t B, int32_t T, int32_t* T_batch,
+                            void* stream_v) {
+    if (!t_solve || !T_batch || B <= 0 || T < 1) return NASTAR_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    batch_steps_kernel<<<1, 256, 0, stream>>>(t_solve, n_steps, B, T, T_batch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
+}
+
+uint64_t nastar_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* nastar_b200_status_string(int s) {
+    switch (s) {
+        case NASTAR_OK: return "ok";
+        case NASTAR_EINVAL: return "invalid argument";
+        case NASTAR_EUNSUPPORTED: return "unsupported map shape or feature";
+        case NASTAR_ECUDA: return "CUDA runtime error";
+        case NASTAR_EWORKSPACE: return "workspace too small";
+        default: return "unknown status";
+    }
+}
+
+const char* nastar_b200_last_cuda_error(void) { return cudaGetErrorString(g_last_err); }
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// nastar_common.cuh — device helpers shared by the A* engines (sm_100a).
+//
+// Arithmetic contract: every fp32 operation of the reference's loop is a
+// separately rounded IEEE op (ATen element-wise kernels; no FMA contraction), so all
+// numerics that feed comparisons go through __fmul_rn/__fadd_rn/__fsqrt_rn here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nastar {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kKeyInf = 0xFFFFFFFFu;  // "no open cell" sentinel, above every float key
+
+// Order-preserving map float -> uint32 (a < b  <=>  key(a) < key(b) for non-NaN a, b).
+__device__ __forceinline__ uint32_t fkey(float f) {
+    uint32_t b = __float_as_uint(f);
+    return b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+}
+
+// f = g_ratio*g + (1-g_ratio)*h   (differentiable_astar.py:206) — three roundings.
+__device__ __forceinline__ float f_value(float gr, float omg, float g, float h) {
+    return __fadd_rn(__fmul_rn(gr, g), __fmul_rn(omg, h));
+}
+
+// get_heuristic (differentiable_astar.py:26-52): chebyshev + 0.001 * euclid, all in fp32.
+__device__ __forceinline__ float heuristic(int y, int x, int gy, int gx) {
+    int idy = y - gy, idx = x - gx;
+    int ady = idy < 0 ? -idy : idy, adx = idx < 0 ? -idx : idx;
+    float cheb = static_cast<float>(ady + adx - (ady < adx ? ady : adx));   // exact
+    float euc = __fsqrt_rn(static_cast<float>(ady * ady + adx * adx));       // exact int -> IEEE sqrt
+    return __fadd_rn(cheb, __fmul_rn(0.001f, euc));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) -------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace nastar

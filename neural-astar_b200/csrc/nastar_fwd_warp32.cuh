@@ -1,0 +1,282 @@
+// nastar_fwd_warp32.cuh — warp-resident forward engine for maps with H <= 32 and W <= 32.
+//
+// Replaces the T-step loop + backtrack of DifferentiableAstar.forward
+// (/root/reference/src/neural_astar/planner/differentiable_astar.py:187-255) for one map per
+// warp.  Design (DESIGN.md "warp32 engine"):
+//   * lane y owns grid row y: passable / open / closed rows are 32-bit masks in registers,
+//     and the lane caches its row's best open cell (order-preserving f key, column).
+//   * node selection (:206-209, softmax+argmax == arg-min of (f, flat index), App. A.2) is
+//     one REDUX.MIN over the 32 cached row minima + a ballot for the lowest row.
+//   * expansion (:228-249) touches <= 8 cells in rows r-1..r+1; those three lanes relax their
+//     <= 3 cells from shared memory (g, h, f, parent planes) and fold the new f keys into their
+//     cached row minimum — insertions/decreases never need a rescan.
+//   * only row r lost its minimum (the selected cell): all 32 lanes rescan that one row
+//     (one conflict-free LDS + REDUX.MIN), overlapped with the g2 dependency chain.
+//   * planes are staged once per map with 1-D TMA bulk copies (cp.async.bulk + mbarrier) and
+//     results leave as coalesced 128-bit stores; the loop never touches HBM.
+#pragma once
+#include "../../include/nastar_b200.h"
+#include "nastar_common.cuh"
+
+namespace nastar {
+
+struct Warp32Smem {
+    // byte offsets inside dynamic shared memory for a map of N cells
+    int n_pad;
+    __host__ __device__ static int npad(int N) { return (N + 3) & ~3; }
+    // words per bit array: flat N-bit plane + 1 pad word, and at least one word per lane/row
+    __host__ __device__ static int bitwords(int N) {
+        const int w = ((N + 31) >> 5) + 1;
+        return w < 32 ? 32 : w;
+    }
+    __host__ __device__ static size_t bytes(int N) {
+        const int np = npad(N);
+        // cost, g, h, f (fp32) + parent (u16) + 2 bit arrays + mbarrier (8 B, 8-B aligned)
+        return size_t(np) * 4 * 4 + size_t(np) * 2 + size_t(2) * bitwords(N) * 4 + 16;
+    }
+};
+
+// Stage one fp32 plane into shared memory. TMA bulk copy when 16-B aligned, LDG/STS otherwise.
+// Returns the number of bytes put in flight on the mbarrier (0 if copied synchronously).
+__device__ __forceinline__ uint32_t stage_plane(float* dst, const float* src, int N, bool tma_ok, int lane) {
+    if (tma_ok) return uint32_t(N) * 4u;
+    for (int i = lane; i < N; i += 32) dst[i] = __ldg(src + i);
+    return 0u;
+}
+
+template <bool kTrace>
+__global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x;
+    const int H = p.H, W = p.W, N = H * W;
+    const int np = Warp32Smem::npad(N);
+    const int nwords = (N + 31) >> 5;
+
+    float* sCost = reinterpret_cast<float*>(smem_raw);
+    float* sG = sCost + np;
+    float* sH = sG + np;
+    float* sF = sH + np;
+    uint16_t* sPar = reinterpret_cast<uint16_t*>(sF + np);
+    uint32_t* sBitsA = reinterpret_cast<uint32_t*>(sPar + np);  // obstacle flat bits, later closed rows
+    uint32_t* sBitsB = sBitsA + Warp32Smem::bitwords(N);        // path rows
+    uint64_t* bar = reinterpret_cast<uint64_t*>(
+        (reinterpret_cast<uintptr_t>(sBitsB + Warp32Smem::bitwords(N)) + 7) & ~uintptr_t(7));
+
+    const float* gCost = p.cost + int64_t(b) * p.cost_stride;
+    const float* gStart = p.start + int64_t(b) * p.start_stride;
+    const float* gGoal = p.goal + int64_t(b) * p.goal_stride;
+    const float* gObst = p.obst + int64_t(b) * p.obst_stride;
+    const bool obst_is_cost = (gObst == gCost);
+
+    // ---------------- prologue: stage planes (TMA), build masks and h ----------------------
+    const bool size_ok = ((N & 3) == 0);
+    const bool t_cost = size_ok && aligned16(gCost);
+    const bool t_start = size_ok && aligned16(gStart);
+    const bool t_goal = size_ok && aligned16(gGoal);
+    const bool t_obst = size_ok && aligned16(gObst) && !obst_is_cost;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    uint32_t tx = 0;
+    tx += stage_plane(sCost, gCost, N, t_cost, lane);
+    tx += stage_plane(sF, gStart, N, t_start, lane);   // start plane parked in the f plane
+    tx += stage_plane(sH, gGoal, N, t_goal, lane);     // goal plane parked in the h plane
+    if (!obst_is_cost) tx += stage_plane(sG, gObst, N, t_obst, lane);  // obstacles parked in g
+    if (tx) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, tx);
+            if (t_cost) tma_load_1d(sCost, gCost, uint32_t(N) * 4u, bar);
+            if (t_start) tma_load_1d(sF, gStart, uint32_t(N) * 4u, bar);
+            if (t_goal) tma_load_1d(sH, gGoal, uint32_t(N) * 4u, bar);
+            if (t_obst) tma_load_1d(sG, gObst, uint32_t(N) * 4u, bar);
+        }
+        mbar_wait(bar, 0);
+    }
+    __syncwarp();
+
+    const float* sObst = obst_is_cost ? sCost : sG;
+    int start_idx = -1, goal_idx = -1;
+    for (int w = 0; w < nwords; ++w) {
+        const int i = (w << 5) + lane;
+        const bool in = i < N;
+        const float vo = in ? sObst[i] : 0.f;
+        const float vs = in ? sF[i] : 0.f;
+        const float vg = in ? sH[i] : 0.f;
+        const uint32_t wo = __ballot_sync(kFull, vo != 0.f);
+        const uint32_t ws = __ballot_sync(kFull, vs != 0.f);
+        const uint32_t wg = __ballot_sync(kFull, vg != 0.f);
+        if (lane == 0) sBitsA[w] = wo;
+        if (start_idx < 0 && ws) start_idx = (w << 5) + __ffs(ws) - 1;
+        if (goal_idx < 0 && wg) goal_idx = (w << 5) + __ffs(wg) - 1;
+    }
+    if (lane == 0) sBitsA[nwords] = 0u;
+    if (goal_idx < 0) goal_idx = 0;  // argmax of an all-zero plane (differentiable_astar.py:197)
+    __syncwarp();
+
+    const uint32_t rowmask = (W == 32) ? 0xFFFFFFFFu : ((1u << W) - 1u);
+    uint32_t pass = 0u;
+    if (lane < H) {
+        const int bit0 = lane * W;
+        pass = __funnelshift_r(sBitsA[bit0 >> 5], sBitsA[(bit0 >> 5) + 1], bit0 & 31) & rowmask;
+    }
+    const int gy = goal_idx / W, gx = goal_idx - gy * W;
+    __syncwarp();
+    // h = heuristic + cost (differentiable_astar.py:191-192); overwrites the parked goal plane
+    {
+        int y = 0, x = lane;
+        while (x >= W) { x -= W; ++y; }
+        for (int i = lane; i < N; i += 32) {
+            sH[i] = __fadd_rn(heuristic(y, x, gy, gx), sCost[i]);
+            x += 32;
+            while (x >= W) { x -= W; ++y; }
+        }
+    }
+    __syncwarp();
+
+    const float gr = p.g_ratio, omg = p.one_minus_g_ratio;
+    uint32_t open = 0u, closed = 0u;
+    uint32_t rm_key = kKeyInf;
+    int rm_col = 0;
+    if (lane == 0) sPar[goal_idx] = uint16_t(goal_idx);  // parents initialised to the goal index (:195-198)
+    if (start_idx >= 0) {
+        const int sy = start_idx / W, sx = start_idx - sy * W;
+        const float f0 = f_value(gr, omg, 0.f, sH[start_idx]);
+        if (lane == 0) {
+            sPar[start_idx] = uint16_t(goal_idx);
+            sG[start_idx] = 0.f;                   // g = 0 (:193); only ever read for opened cells
+            sF[start_idx] = f0;
+        }
+        if (lane == sy) {
+            open = 1u << sx;                       // open_maps = start_maps (:187)
+            rm_key = fkey(f0);
+            rm_col = sx;
+        }
+    }
+    __syncwarp();
+
+    // ---------------- the search loop (differentiable_astar.py:203-252) --------------------
+    const int T = p.T;
+    int t_solve = NASTAR_TS_CAPPED;
+    int steps = 0;
+    int32_t* trace = kTrace ? (p.trace + int64_t(b) * T) : nullptr;
+    for (int t = 0; t < T; ++t) {
+        // -- select: arg-min over (f key, row, col) ------------------------------------------
+        const uint32_t m = __reduce_min_sync(kFull, rm_key);
+        if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
+        const int r = __ffs(__ballot_sync(kFull, rm_key == m)) - 1;
+        const int c = __shfl_sync(kFull, rm_col, r);
+        const int ind = r * W + c;
+        steps = t + 1;
+        if (kTrace && lane == 0) trace[t] = ind;
+        const bool solved = (ind == goal_idx);              // :219-220
+        // -- closed/open update of the selected cell (:222-225) ------------------------------
+        if (lane == r) {
+            closed |= 1u << c;
+            if (!solved) open &= ~(1u << c);                // the goal stays open once selected
+            rm_key = kKeyInf;                               // this row's minimum is rebuilt below
+        }
+        // -- rescan of row r over its remaining (pre-expansion) open cells --------------------
+        const uint32_t open_r = __shfl_sync(kFull, open, r);
+        uint32_t rs_key = kKeyInf;
+        if ((open_r >> lane) & 1u) rs_key = fkey(sF[ind - c + lane]);
+        // -- expansion: rows r-1..r+1, columns c-1..c+1 (:228-249) ---------------------------
+        const int dr = lane - r;
+        uint32_t win = (c == 0) ? 3u : (7u << (c - 1));
+        if (dr == 0) win &= ~(1u << c);
+        const uint32_t cand = (dr >= -1 && dr <= 1) ? (win & pass) : 0u;
+        float gn[3], hn[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int x = c - 1 + k;
+            const bool on = (unsigned(x) < 32u) && ((cand >> (x & 31)) & 1u);
+            const int n = lane * W + x;
+            gn[k] = on ? sG[n] : 0.f;
+            hn[k] = on ? sH[n] : 0.f;
+        }
+        const float g2 = __fadd_rn(sG[ind], sCost[ind]);    // :234, cost of the SELECTED node
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int x = c - 1 + k;
+            const bool on = (unsigned(x) < 32u) && ((cand >> (x & 31)) & 1u);
+            if (on) {
+                const uint32_t bit = 1u << x;
+                // :235-236  idx = (1-open)(1-hist) + open*(g > g2), masked by passable neighbours
+                const bool upd = (open & bit) ? (gn[k] > g2) : !(closed & bit);
+                if (upd) {
+                    const int n = lane * W + x;
+                    const float fn = f_value(gr, omg, g2, hn[k]);
+                    sG[n] = g2;                              // :238
+                    sF[n] = fn;
+                    sPar[n] = uint16_t(ind);                 // :246-249
+                    open |= bit;                             // :242
+                    const uint32_t key = fkey(fn);
+                    if (key < rm_key || (key == rm_key && x < rm_col)) { rm_key = key; rm_col = x; }
+                }
+            }
+        }
+        if (solved) { t_solve = t; break; }                 // :251-252 (per-map early exit, App. A.4)
+        // -- fold the rescan into lane r's cached minimum -------------------------------------
+        const uint32_t mr = __reduce_min_sync(kFull, rs_key);
+        const int mc = __ffs(__ballot_sync(kFull, rs_key == mr)) - 1;
+        if (lane == r && (mr < rm_key || (mr == rm_key && mc < rm_col))) { rm_key = mr; rm_col = mc; }
+        __syncwarp();
+    }
+    __syncwarp();
+
+    // ---------------- backtrack (differentiable_astar.py:96-125, App. A.3) ------------------
+    uint32_t path = 0u;
+    {
+        const int gyy = goal_idx / W;
+        if (lane == gyy) path |= 1u << (goal_idx - gyy * W);
+        int loc = sPar[goal_idx];
+        const int hops = (t_solve >= 0) ? N : (T - 1);
+        for (int k = 0; k < hops; ++k) {
+            const int y = loc / W;
+            if (lane == y) path |= 1u << (loc - y * W);
+            if (loc == start_idx || loc == goal_idx) break;  // reached the start (or a self-loop)
+            loc = sPar[loc];
+        }
+    }
+
+    // ---------------- epilogue: coalesced stores of histories / paths -----------------------
+    sBitsA[lane] = closed;
+    sBitsB[lane] = path;
+    __syncwarp();
+    float* gHist = p.histories + int64_t(b) * N;
+    long long* gPath = reinterpret_cast<long long*>(p.paths) + int64_t(b) * N;
+    if ((W & 3) == 0 && aligned16(gHist) && aligned16(gPath)) {
+        const int n4 = N >> 2;
+        int y = 0, x = lane << 2;
+        while (x >= W) { x -= W; ++y; }
+        for (int i4 = lane; i4 < n4; i4 += 32) {
+            const uint32_t cb = sBitsA[y] >> x, pb = sBitsB[y] >> x;
+            float4 hv = make_float4((cb & 1u) ? 1.f : 0.f, (cb & 2u) ? 1.f : 0.f, (cb & 4u) ? 1.f : 0.f,
+                                    (cb & 8u) ? 1.f : 0.f);
+            reinterpret_cast<float4*>(gHist)[i4] = hv;
+            longlong2 p0 = make_longlong2((pb & 1u) ? 1ll : 0ll, (pb & 2u) ? 1ll : 0ll);
+            longlong2 p1 = make_longlong2((pb & 4u) ? 1ll : 0ll, (pb & 8u) ? 1ll : 0ll);
+            reinterpret_cast<longlong2*>(gPath)[2 * i4] = p0;
+            reinterpret_cast<longlong2*>(gPath)[2 * i4 + 1] = p1;
+            x += 128;
+            while (x >= W) { x -= W; ++y; }
+        }
+    } else {
+        int y = 0, x = lane;
+        while (x >= W) { x -= W; ++y; }
+        for (int i = lane; i < N; i += 32) {
+            gHist[i] = ((sBitsA[y] >> x) & 1u) ? 1.f : 0.f;
+            gPath[i] = ((sBitsB[y] >> x) & 1u) ? 1ll : 0ll;
+            x += 32;
+            while (x >= W) { x -= W; ++y; }
+        }
+    }
+    if (lane == 0) {
+        if (p.t_solve) p.t_solve[b] = t_solve;
+        if (p.n_steps) p.n_steps[b] = steps;
+    }
+}
+
+}  // namespace nastar

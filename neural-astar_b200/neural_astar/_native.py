@@ -1,0 +1,238 @@
+"""ctypes binding of libnastar_b200.so (C ABI declared in include/nastar_b200.h).
+
+PyTorch is used here only for device memory and the current CUDA stream; the library itself
+has no torch dependency.  Loading fails loudly when the library is missing: the product has no
+CPU or eager-PyTorch fallback for the search.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # neural-astar_b200/
+LIB_PATH = os.environ.get("NASTAR_B200_LIB", os.path.join(_PKG_ROOT, "lib", "libnastar_b200.so"))
+
+ABI_VERSION = 1
+NASTAR_OK = 0
+TS_CAPPED = -1
+TS_EXHAUSTED = -2
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+class FwdParams(ctypes.Structure):
+    """struct nastar_fwd_params (include/nastar_b200.h)"""
+
+    _fields_ = [
+        ("cost", ctypes.c_void_p), ("cost_stride", ctypes.c_int64),
+        ("start", ctypes.c_void_p), ("start_stride", ctypes.c_int64),
+        ("goal", ctypes.c_void_p), ("goal_stride", ctypes.c_int64),
+        ("obst", ctypes.c_void_p), ("obst_stride", ctypes.c_int64),
+        ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+        ("g_ratio", ctypes.c_float), ("one_minus_g_ratio", ctypes.c_float),
+        ("T", ctypes.c_int32),
+        ("histories", ctypes.c_void_p), ("paths", ctypes.c_void_p),
+        ("t_solve", ctypes.c_void_p), ("n_steps", ctypes.c_void_p), ("trace", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
+class BwdParams(ctypes.Structure):
+    """struct nastar_bwd_params (include/nastar_b200.h)"""
+
+    _fields_ = [
+        ("cost", ctypes.c_void_p), ("cost_stride", ctypes.c_int64),
+        ("start", ctypes.c_void_p), ("start_stride", ctypes.c_int64),
+        ("goal", ctypes.c_void_p), ("goal_stride", ctypes.c_int64),
+        ("obst", ctypes.c_void_p), ("obst_stride", ctypes.c_int64),
+        ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+        ("g_ratio", ctypes.c_float), ("one_minus_g_ratio", ctypes.c_float), ("sqrt_w", ctypes.c_float),
+        ("T_batch", ctypes.c_void_p),
+        ("grad_histories", ctypes.c_void_p), ("grad_stride", ctypes.c_int64),
+        ("grad_cost", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
+EXPORTS = (
+    "nastar_b200_abi_version",
+    "nastar_b200_forward_workspace_bytes",
+    "nastar_b200_backward_workspace_bytes",
+    "nastar_b200_forward",
+    "nastar_b200_backward",
+    "nastar_b200_batch_steps",
+    "nastar_b200_engine_for",
+    "nastar_b200_launch_count",
+    "nastar_b200_status_string",
+    "nastar_b200_last_cuda_error",
+)
+
+_lib = None
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def lib():
+    """Load the engine. Raises NativeLibraryMissing (never falls back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: build the sm_100a engine first "
+            "(python -c 'import __graft_entry__ as g; g.build()' or make -C neural-astar_b200). "
+            "neural_astar (B200) has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    L.nastar_b200_abi_version.restype = ctypes.c_int
+    L.nastar_b200_forward_workspace_bytes.argtypes = [ctypes.c_int32] * 3
+    L.nastar_b200_forward_workspace_bytes.restype = ctypes.c_size_t
+    L.nastar_b200_backward_workspace_bytes.argtypes = [ctypes.c_int32] * 3
+    L.nastar_b200_backward_workspace_bytes.restype = ctypes.c_size_t
+    L.nastar_b200_forward.argtypes = [ctypes.POINTER(FwdParams), ctypes.c_void_p]
+    L.nastar_b200_forward.restype = ctypes.c_int
+    L.nastar_b200_backward.argtypes = [ctypes.POINTER(BwdParams), ctypes.c_void_p]
+    L.nastar_b200_backward.restype = ctypes.c_int
+    L.nastar_b200_batch_steps.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+    L.nastar_b200_batch_steps.restype = ctypes.c_int
+    L.nastar_b200_engine_for.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    L.nastar_b200_engine_for.restype = ctypes.c_int
+    L.nastar_b200_launch_count.restype = ctypes.c_uint64
+    L.nastar_b200_status_string.argtypes = [ctypes.c_int]
+    L.nastar_b200_status_string.restype = ctypes.c_char_p
+    L.nastar_b200_last_cuda_error.restype = ctypes.c_char_p
+    if L.nastar_b200_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI {L.nastar_b200_abi_version()} != expected {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def _check(status: int, what: str) -> None:
+    if status != NASTAR_OK:
+        L = lib()
+        msg = L.nastar_b200_status_string(status).decode()
+        if status == 3:
+            msg += ": " + L.nastar_b200_last_cuda_error().decode()
+        raise RuntimeError(f"{what} failed: {msg}")
+
+
+def host_scalars(g_ratio: float, W: int) -> Tuple[float, float, float]:
+    """The Python-double scalar arithmetic of differentiable_astar.py:206-207; ctypes then rounds
+    each to fp32 exactly as ATen rounds a Python scalar operand."""
+    return float(g_ratio), float(1 - g_ratio), math.sqrt(W)
+
+
+def _plane(x: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
+    """Return (tensor kept alive, device pointer of channel 0, map stride in elements)."""
+    if x.dtype != torch.float32:
+        raise TypeError(f"planes must be float32 (got {x.dtype}); the reference path is fp32-only")
+    H, W = x.shape[-2], x.shape[-1]
+    if x.stride(-1) != 1 or x.stride(-2) != W:
+        x = x.contiguous()
+    return x, x.data_ptr(), x.stride(0)
+
+
+def launch_count() -> int:
+    return int(lib().nastar_b200_launch_count())
+
+
+def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: torch.Tensor,
+            g_ratio: float, T: int, want_trace: bool = False):
+    """Run the search for a batch of [B,C,H,W] fp32 CUDA planes (channel 0 is used).
+
+    Returns (histories [B,1,H,W] f32, paths [B,1,H,W] i64, t_solve [B] i32, n_steps [B] i32,
+    trace [B,T] i32 or None), all on the inputs' device, asynchronously on the current stream.
+    """
+    L = lib()
+    if not cost.is_cuda:
+        raise RuntimeError("neural_astar (B200): the search runs on CUDA tensors only (no CPU fallback); "
+                           "move the planner inputs to the GPU")
+    dev = cost.device
+    for t_ in (start, goal, obst):
+        if t_.device != dev:
+            raise RuntimeError("all planes must live on the same CUDA device")
+    B, _, H, W = cost.shape
+    for t_ in (start, goal, obst):
+        if t_.shape[0] != B or t_.shape[-2:] != (H, W):
+            raise ValueError("plane shapes differ")
+    keep = []
+    p = FwdParams()
+    for name, t_ in (("cost", cost.detach()), ("start", start.detach()), ("goal", goal.detach()),
+                     ("obst", obst.detach())):
+        k, ptr, stride = _plane(t_)
+        keep.append(k)
+        setattr(p, name, ptr)
+        setattr(p, name + "_stride", stride)
+    gr, omg, _ = host_scalars(g_ratio, W)
+    p.B, p.H, p.W = B, H, W
+    p.g_ratio, p.one_minus_g_ratio = gr, omg
+    p.T = int(T)
+    with torch.cuda.device(dev):
+        hist = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        paths = torch.empty((B, 1, H, W), dtype=torch.int64, device=dev)
+        t_solve = torch.empty((B,), dtype=torch.int32, device=dev)
+        n_steps = torch.empty((B,), dtype=torch.int32, device=dev)
+        trace = torch.empty((B, int(T)), dtype=torch.int32, device=dev) if want_trace else None
+        ws_bytes = L.nastar_b200_forward_workspace_bytes(B, H, W)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+        p.histories, p.paths = hist.data_ptr(), paths.data_ptr()
+        p.t_solve, p.n_steps = t_solve.data_ptr(), n_steps.data_ptr()
+        p.trace = trace.data_ptr() if want_trace else None
+        p.workspace = ws.data_ptr() if ws is not None else None
+        p.workspace_bytes = ws_bytes
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(L.nastar_b200_forward(ctypes.byref(p), ctypes.c_void_p(stream)), "nastar_b200_forward")
+    del keep
+    return hist, paths, t_solve, n_steps, trace
+
+
+def batch_steps(t_solve: torch.Tensor, n_steps: torch.Tensor, T: int) -> torch.Tensor:
+    """Device-side T_batch (int32[1]); replaces the per-step host sync of differentiable_astar.py:251."""
+    L = lib()
+    dev = t_solve.device
+    with torch.cuda.device(dev):
+        out = torch.empty((1,), dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(L.nastar_b200_batch_steps(t_solve.data_ptr(), n_steps.data_ptr(), t_solve.numel(), int(T),
+                                         out.data_ptr(), ctypes.c_void_p(stream)), "nastar_b200_batch_steps")
+    return out
+
+
+def backward(cost, start, goal, obst, grad_hist: torch.Tensor, T_batch: torch.Tensor, g_ratio: float) -> torch.Tensor:
+    """dL/dcost [B,1,H,W] from dL/dhistories (closed form of the reference's autograd)."""
+    L = lib()
+    dev = cost.device
+    B, _, H, W = cost.shape
+    keep = []
+    p = BwdParams()
+    for name, t_ in (("cost", cost.detach()), ("start", start.detach()), ("goal", goal.detach()),
+                     ("obst", obst.detach())):
+        k, ptr, stride = _plane(t_)
+        keep.append(k)
+        setattr(p, name, ptr)
+        setattr(p, name + "_stride", stride)
+    gh, ptr, stride = _plane(grad_hist.detach().to(torch.float32))
+    keep.append(gh)
+    p.grad_histories, p.grad_stride = ptr, stride
+    gr, omg, sq = host_scalars(g_ratio, W)
+    p.B, p.H, p.W = B, H, W
+    p.g_ratio, p.one_minus_g_ratio, p.sqrt_w = gr, omg, sq
+    p.T_batch = T_batch.data_ptr()
+    with torch.cuda.device(dev):
+        grad_cost = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        ws_bytes = L.nastar_b200_backward_workspace_bytes(B, H, W)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
+        p.grad_cost = grad_cost.data_ptr()
+        p.workspace = ws.data_ptr() if ws is not None else None
+        p.workspace_bytes = ws_bytes
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(L.nastar_b200_backward(ctypes.byref(p), ctypes.c_void_p(stream)), "nastar_b200_backward")
+    del keep
+    return grad_cost
