@@ -5,11 +5,30 @@
 #include <cstdio>
 
 #include "../../include/nastar_b200.h"
+#include "nastar_fwd_generic.cuh"
 #include "nastar_fwd_warp32.cuh"
 
 namespace {
 std::atomic<uint64_t> g_launches{0};
 cudaError_t g_last_err = cudaSuccess;
+
+constexpr size_t kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+constexpr int kGlobalCtasPerSm = 6;
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+int generic_slots(int B) {
+    const int cap = num_sms() * kGlobalCtasPerSm;
+    return B < cap ? B : cap;
+}
 
 inline int cuda_fail(cudaError_t e) {
     g_last_err = e;
@@ -47,12 +66,16 @@ int nastar_b200_abi_version(void) { return NASTAR_B200_ABI_VERSION; }
 int nastar_b200_engine_for(int32_t H, int32_t W) {
     if (H <= 0 || W <= 0) return 0;
     if (H <= 32 && W <= 32) return 1;
+    if (int64_t(H) * W > (int64_t(1) << 30)) return 0;
+    const nastar::GenericLayout L(H, W);
+    if (L.smem_common() + L.smem_planes() <= kMaxDynSmem) return 2;
+    if (L.smem_common() <= kMaxDynSmem) return 3;
     return 0;
 }
 
 size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
-    (void)B; (void)H; (void)W;
-    return 0;
+    if (B <= 0 || nastar_b200_engine_for(H, W) != 3) return 0;
+    return size_t(generic_slots(B)) * nastar::GenericLayout(H, W).slot_bytes();
 }
 
 size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
@@ -77,6 +100,26 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
             nastar::astar_fwd_warp32_kernel<true><<<p->B, 32, smem, stream>>>(*p);
         else
             nastar::astar_fwd_warp32_kernel<false><<<p->B, 32, smem, stream>>>(*p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+        const nastar::GenericLayout L(p->H, p->W);
+        const bool global = (engine == 3);
+        const size_t smem = L.smem_common() + (global ? 0 : L.smem_planes());
+        int grid = p->B;
+        if (global) {
+            grid = generic_slots(p->B);
+            if (!p->workspace || p->workspace_bytes < size_t(grid) * L.slot_bytes()) return NASTAR_EWORKSPACE;
+        }
+        auto launch = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            kernel<<<grid, 32, smem, stream>>>(*p);
+            return cudaSuccess;
+        };
+        cudaError_t e;
+        if (global) e = p->trace ? launch(nastar::astar_fwd_generic_kernel<true, true>) : launch(nastar::astar_fwd_generic_kernel<true, false>);
+        else e = p->trace ? launch(nastar::astar_fwd_generic_kernel<false, true>) : launch(nastar::astar_fwd_generic_kernel<false, false>);
+        if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     cudaError_t e = cudaGetLastError();
