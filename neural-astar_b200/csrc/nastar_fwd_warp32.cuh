@@ -162,66 +162,75 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
     int t_solve = NASTAR_TS_CAPPED;
     int steps = 0;
     int32_t* trace = kTrace ? (p.trace + int64_t(b) * T) : nullptr;
+    uint32_t* sOpenRow = sBitsB;   // shared copy of every lane's open row (rescan reads row r's)
+    sOpenRow[lane] = open;
+    __syncwarp();
+    const int rowbase = lane * W;
     for (int t = 0; t < T; ++t) {
-        // -- select: arg-min over (f key, row, col) ------------------------------------------
+        // -- select: lexicographic arg-min of (f key, row, col) with two REDUX.MINs -----------
         const uint32_t m = __reduce_min_sync(kFull, rm_key);
         if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
-        const int r = __ffs(__ballot_sync(kFull, rm_key == m)) - 1;
-        const int c = __shfl_sync(kFull, rm_col, r);
+        const uint32_t selrc = __reduce_min_sync(kFull, (rm_key == m) ? uint32_t((lane << 5) | rm_col) : 0xFFFFFFFFu);
+        const int r = int(selrc >> 5), c = int(selrc & 31u);
         const int ind = r * W + c;
         steps = t + 1;
         if (kTrace && lane == 0) trace[t] = ind;
         const bool solved = (ind == goal_idx);              // :219-220
+        const uint32_t cbit = 1u << c;
+        // -- rescan inputs for row r (pre-expansion open cells minus the selected one); stale f
+        //    values of cells relaxed this step are upper bounds and the fresh keys are merged below
+        const uint32_t open_r = sOpenRow[r] & ~cbit;
+        const float frs = sF[ind - c + lane];
+        const uint32_t rs_key = ((open_r >> lane) & 1u) ? fkey(frs) : kKeyInf;
         // -- closed/open update of the selected cell (:222-225) ------------------------------
-        if (lane == r) {
-            closed |= 1u << c;
-            if (!solved) open &= ~(1u << c);                // the goal stays open once selected
+        const int dr = lane - r;
+        if (dr == 0) {
+            closed |= cbit;
+            if (!solved) open &= ~cbit;                     // the goal stays open once selected
             rm_key = kKeyInf;                               // this row's minimum is rebuilt below
         }
-        // -- rescan of row r over its remaining (pre-expansion) open cells --------------------
-        const uint32_t open_r = __shfl_sync(kFull, open, r);
-        uint32_t rs_key = kKeyInf;
-        if ((open_r >> lane) & 1u) rs_key = fkey(sF[ind - c + lane]);
-        // -- expansion: rows r-1..r+1, columns c-1..c+1 (:228-249) ---------------------------
-        const int dr = lane - r;
+        // -- expansion: rows r-1..r+1, columns c-1..c+1 (:228-249), branch-free ---------------
         uint32_t win = (c == 0) ? 3u : (7u << (c - 1));
-        if (dr == 0) win &= ~(1u << c);
-        const uint32_t cand = (dr >= -1 && dr <= 1) ? (win & pass) : 0u;
+        if (dr == 0) win &= ~cbit;
+        const bool near = (dr >= -1) & (dr <= 1);
+        const uint32_t cand = near ? (win & pass) : 0u;
         float gn[3], hn[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int x = c - 1 + k;
-            const bool on = (unsigned(x) < 32u) && ((cand >> (x & 31)) & 1u);
-            const int n = lane * W + x;
-            gn[k] = on ? sG[n] : 0.f;
-            hn[k] = on ? sH[n] : 0.f;
+            const bool on = (cand >> (x & 31)) & 1u;        // cand has no bit for x = -1 or 32
+            gn[k] = on ? sG[rowbase + x] : 0.f;
+            hn[k] = on ? sH[rowbase + x] : 0.f;
         }
         const float g2 = __fadd_rn(sG[ind], sCost[ind]);    // :234, cost of the SELECTED node
+        const float ag = __fmul_rn(gr, g2);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const int x = c - 1 + k;
-            const bool on = (unsigned(x) < 32u) && ((cand >> (x & 31)) & 1u);
-            if (on) {
-                const uint32_t bit = 1u << x;
-                // :235-236  idx = (1-open)(1-hist) + open*(g > g2), masked by passable neighbours
-                const bool upd = (open & bit) ? (gn[k] > g2) : !(closed & bit);
-                if (upd) {
-                    const int n = lane * W + x;
-                    const float fn = f_value(gr, omg, g2, hn[k]);
-                    sG[n] = g2;                              // :238
-                    sF[n] = fn;
-                    sPar[n] = uint16_t(ind);                 // :246-249
-                    open |= bit;                             // :242
-                    const uint32_t key = fkey(fn);
-                    if (key < rm_key || (key == rm_key && x < rm_col)) { rm_key = key; rm_col = x; }
-                }
+            const uint32_t bit = 1u << (x & 31);
+            const bool on = (cand & bit) != 0u;
+            // :235-236  idx = (1-open)(1-hist) + open*(g > g2), masked by passable neighbours
+            const bool upd = on & (((open & bit) != 0u) ? (gn[k] > g2) : ((closed & bit) == 0u));
+            const float fn = __fadd_rn(ag, __fmul_rn(omg, hn[k]));
+            const uint32_t key = fkey(fn);
+            if (upd) {
+                sG[rowbase + x] = g2;                        // :238
+                sF[rowbase + x] = fn;
+                sPar[rowbase + x] = uint16_t(ind);           // :246-249
             }
+            open |= upd ? bit : 0u;                          // :242
+            const bool better = upd & ((key < rm_key) | ((key == rm_key) & (x < rm_col)));
+            rm_key = better ? key : rm_key;
+            rm_col = better ? x : rm_col;
         }
         if (solved) { t_solve = t; break; }                 // :251-252 (per-map early exit, App. A.4)
+        if (near) sOpenRow[lane] = open;
         // -- fold the rescan into lane r's cached minimum -------------------------------------
         const uint32_t mr = __reduce_min_sync(kFull, rs_key);
-        const int mc = __ffs(__ballot_sync(kFull, rs_key == mr)) - 1;
-        if (lane == r && (mr < rm_key || (mr == rm_key && mc < rm_col))) { rm_key = mr; rm_col = mc; }
+        const uint32_t mc = __reduce_min_sync(kFull, (rs_key == mr) ? uint32_t(lane) : 0xFFFFFFFFu);
+        const bool take = (dr == 0) & ((mr < rm_key) | ((mr == rm_key) & (int(mc) < rm_col)));
+        rm_key = take ? mr : rm_key;
+        rm_col = take ? int(mc) : rm_col;
         __syncwarp();
     }
     __syncwarp();
