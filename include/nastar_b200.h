@@ -81,6 +81,7 @@ typedef struct nastar_bwd_params {
        DEVICE from *T_batch so that no host synchronisation is needed between forward
        and backward */
     const int32_t *T_batch;
+    const int32_t *t_solve;   /* [B] the forward's t_solve[] for the same inputs and loop bound */
     const float *grad_histories; int64_t grad_stride; /* dL/d histories, [B][H*W] */
     float *grad_cost;                                  /* dL/d cost_maps, [B][H*W], overwritten */
     void  *workspace;

@@ -96,10 +96,12 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
     }
     if (engine == 1) {
         const size_t smem = nastar::Warp32Smem::bytes(N);
+        nastar::W32Args a{};
+        a.f = *p;
         if (p->trace)
-            nastar::astar_fwd_warp32_kernel<true><<<p->B, 32, smem, stream>>>(*p);
+            nastar::astar_warp32_kernel<true, false><<<p->B, 32, smem, stream>>>(a);
         else
-            nastar::astar_fwd_warp32_kernel<false><<<p->B, 32, smem, stream>>>(*p);
+            nastar::astar_warp32_kernel<false, false><<<p->B, 32, smem, stream>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
         const nastar::GenericLayout L(p->H, p->W);
@@ -128,8 +130,35 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
 }
 
 int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
-    (void)p; (void)stream_v;
-    return NASTAR_EUNSUPPORTED;
+    if (!p || !p->cost || !p->start || !p->goal || !p->obst || !p->grad_histories || !p->grad_cost || !p->T_batch ||
+        !p->t_solve)
+        return NASTAR_EINVAL;
+    if (p->B <= 0 || p->H <= 0 || p->W <= 0) return NASTAR_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int engine = nastar_b200_engine_for(p->H, p->W);
+    if (engine != 1) return NASTAR_EUNSUPPORTED;   // training configs of the reference are 32x32 / 12x12
+    const int N = p->H * p->W;
+    nastar::W32Args a{};
+    a.f.cost = p->cost;   a.f.cost_stride = p->cost_stride;
+    a.f.start = p->start; a.f.start_stride = p->start_stride;
+    a.f.goal = p->goal;   a.f.goal_stride = p->goal_stride;
+    a.f.obst = p->obst;   a.f.obst_stride = p->obst_stride;
+    a.f.B = p->B; a.f.H = p->H; a.f.W = p->W;
+    a.f.g_ratio = p->g_ratio;
+    a.f.one_minus_g_ratio = p->one_minus_g_ratio;
+    a.f.T = 0;  // the loop bound comes from *T_batch on the device
+    a.sqrt_w = p->sqrt_w;
+    a.T_batch = p->T_batch;
+    a.t_solve_in = p->t_solve;
+    a.grad_hist = p->grad_histories;
+    a.grad_stride = p->grad_stride;
+    a.grad_cost = p->grad_cost;
+    const size_t smem = nastar::Warp32Smem::bytes(N, true);
+    nastar::astar_warp32_kernel<false, true><<<p->B, 32, smem, stream>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
 }
 
 int nastar_b200_batch_steps(const int32_t* t_solve, const int32_t* n_steps, int32_t B, int32_t T, int32_t* T_batch,

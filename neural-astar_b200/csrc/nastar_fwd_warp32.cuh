@@ -29,10 +29,12 @@ struct Warp32Smem {
         const int w = ((N + 31) >> 5) + 1;
         return w < 32 ? 32 : w;
     }
-    __host__ __device__ static size_t bytes(int N) {
+    __host__ __device__ static size_t bytes(int N, bool bwd = false) {
         const int np = npad(N);
         // cost, g, h, f (fp32) + parent (u16) + 2 bit arrays + mbarrier (8 B, 8-B aligned)
-        return size_t(np) * 4 * 4 + size_t(np) * 2 + size_t(2) * bitwords(N) * 4 + 16;
+        // backward adds the softmax-numerator plane v (fp32, padded to a multiple of 128 cells)
+        return size_t(np) * 4 * 4 + size_t(np) * 2 + size_t(2) * bitwords(N) * 4 + 16 +
+               (bwd ? size_t((N + 127) & ~127) * 4 + 16 : 0);
     }
 };
 
@@ -44,8 +46,34 @@ __device__ __forceinline__ uint32_t stage_plane(float* dst, const float* src, in
     return 0u;
 }
 
-template <bool kTrace>
-__global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_params p) {
+// Kernel arguments: the forward parameters plus, for the backward replay, the extra fields of
+// nastar_bwd_params.  One kernel body serves both so that the replay can never drift from the
+// forward's state machine.
+struct W32Args {
+    nastar_fwd_params f;
+    // backward only
+    float sqrt_w;
+    const int32_t* T_batch;       // device scalar: number of loop iterations of the reference
+    const int32_t* t_solve_in;    // forward's t_solve[] (which maps had their goal clamped, App. B)
+    const float* grad_hist;
+    int64_t grad_stride;
+    float* grad_cost;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// kBwd = false: forward search (histories, paths, t_solve, n_steps, optional trace).
+// kBwd = true : replays the same search and accumulates the closed-form gradient
+//               dL/dcost[p] = sum_t -(1-g_ratio)/sqrt(W) * y_t[p] * (Gh[p] - <Gh, y_t>)   
+//               where y_t is the softmax over the open set at step t (differentiable_astar.py:206-209,
+//               :55-74) — the only path the reference's autograd keeps alive (:237-243 detach the rest).
+template <bool kTrace, bool kBwd>
+__global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
+    const nastar_fwd_params& p = a.f;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     const int b = blockIdx.x;
@@ -62,6 +90,9 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
     uint32_t* sBitsB = sBitsA + Warp32Smem::bitwords(N);        // path rows
     uint64_t* bar = reinterpret_cast<uint64_t*>(
         (reinterpret_cast<uintptr_t>(sBitsB + Warp32Smem::bitwords(N)) + 7) & ~uintptr_t(7));
+    // backward: v[i] = exp(-f[i]/sqrt(W)) for open cells, 0 otherwise (dense softmax numerator)
+    float* sV = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bar + 1) + 15) & ~uintptr_t(15));
+    const int nv4 = ((N + 127) & ~127) >> 2;   // float4 count of the padded v plane (multiple of 32)
 
     const float* gCost = p.cost + int64_t(b) * p.cost_stride;
     const float* gStart = p.start + int64_t(b) * p.start_stride;
@@ -141,6 +172,38 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
     uint32_t rm_key = kKeyInf;
     int rm_col = 0;
     if (lane == 0) sPar[goal_idx] = uint16_t(goal_idx);  // parents initialised to the goal index (:195-198)
+    float Gh[32], acc[32];        // backward: upstream gradient / accumulator, cell 4*(lane+32j)+e
+    int Tb = 0, ts_in = NASTAR_TS_CAPPED;
+    if (kBwd) {
+        float4* sV4 = reinterpret_cast<float4*>(sV);
+        for (int q = lane; q < nv4; q += 32) sV4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        Tb = *a.T_batch;
+        ts_in = a.t_solve_in[b];
+        const float* gG = a.grad_hist + int64_t(b) * a.grad_stride;
+        const bool vec = ((N & 3) == 0) && aligned16(gG);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i0 = 4 * (lane + 32 * j);
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec) {
+                if (i0 < N) g4 = __ldg(reinterpret_cast<const float4*>(gG + i0));
+            } else {
+                if (i0 + 0 < N) g4.x = __ldg(gG + i0 + 0);
+                if (i0 + 1 < N) g4.y = __ldg(gG + i0 + 1);
+                if (i0 + 2 < N) g4.z = __ldg(gG + i0 + 2);
+                if (i0 + 3 < N) g4.w = __ldg(gG + i0 + 3);
+            }
+            // clamp(hist + sel) blocks the gradient at a goal that is re-selected after its solve
+            // step (pre-clamp value 2, differentiable_astar.py:222-223)
+            const bool blocked = (ts_in >= 0) && (ts_in < Tb - 1);
+            Gh[4 * j + 0] = (blocked && i0 + 0 == goal_idx) ? 0.f : g4.x;
+            Gh[4 * j + 1] = (blocked && i0 + 1 == goal_idx) ? 0.f : g4.y;
+            Gh[4 * j + 2] = (blocked && i0 + 2 == goal_idx) ? 0.f : g4.z;
+            Gh[4 * j + 3] = (blocked && i0 + 3 == goal_idx) ? 0.f : g4.w;
+            acc[4 * j + 0] = acc[4 * j + 1] = acc[4 * j + 2] = acc[4 * j + 3] = 0.f;
+        }
+        __syncwarp();
+    }
     if (start_idx >= 0) {
         const int sy = start_idx / W, sx = start_idx - sy * W;
         const float f0 = f_value(gr, omg, 0.f, sH[start_idx]);
@@ -148,6 +211,7 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
             sPar[start_idx] = uint16_t(goal_idx);
             sG[start_idx] = 0.f;                   // g = 0 (:193); only ever read for opened cells
             sF[start_idx] = f0;
+            if (kBwd) sV[start_idx] = expf(__fdiv_rn(-f0, a.sqrt_w));   // :207
         }
         if (lane == sy) {
             open = 1u << sx;                       // open_maps = start_maps (:187)
@@ -166,10 +230,44 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
     sOpenRow[lane] = open;
     __syncwarp();
     const int rowbase = lane * W;
-    for (int t = 0; t < T; ++t) {
+    const int Tloop = kBwd ? Tb : T;
+    // post-solve steps are stationary when g_ratio >= 0.5 (the goal keeps being re-selected and
+    // nothing changes): the backward then adds them in one go
+    const bool stationary_ok = (gr >= 0.5f);
+    for (int t = 0; t < Tloop; ++t) {
         // -- select: lexicographic arg-min of (f key, row, col) with two REDUX.MINs -----------
         const uint32_t m = __reduce_min_sync(kFull, rm_key);
         if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
+        if (kBwd) {
+            // y_t = v / sum(v) over the open set at the START of step t; accumulate
+            // y_t[p] * (Gh[p] - <Gh, y_t>)  (times the number of identical post-solve steps)
+            const float4* sV4 = reinterpret_cast<const float4*>(sV);
+            float4 v[8];
+            float s_ = 0.f, d_ = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = (lane + 32 * j < nv4) ? sV4[lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                s_ += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+                d_ = fmaf(Gh[4 * j + 0], v[j].x, d_);
+                d_ = fmaf(Gh[4 * j + 1], v[j].y, d_);
+                d_ = fmaf(Gh[4 * j + 2], v[j].z, d_);
+                d_ = fmaf(Gh[4 * j + 3], v[j].w, d_);
+            }
+            s_ = warp_sum(s_);
+            d_ = warp_sum(d_);
+            const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
+            const float wgt = last ? float(Tb - t) : 1.f;
+            const float inv = wgt / s_;
+            const float dd = d_ / s_;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[4 * j + 0] = fmaf(v[j].x * inv, Gh[4 * j + 0] - dd, acc[4 * j + 0]);
+                acc[4 * j + 1] = fmaf(v[j].y * inv, Gh[4 * j + 1] - dd, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(v[j].z * inv, Gh[4 * j + 2] - dd, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(v[j].w * inv, Gh[4 * j + 3] - dd, acc[4 * j + 3]);
+            }
+            if (last) break;
+        }
         const uint32_t selrc = __reduce_min_sync(kFull, (rm_key == m) ? uint32_t((lane << 5) | rm_col) : 0xFFFFFFFFu);
         const int r = int(selrc >> 5), c = int(selrc & 31u);
         const int ind = r * W + c;
@@ -179,7 +277,7 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
         const uint32_t cbit = 1u << c;
         // -- rescan inputs for row r (pre-expansion open cells minus the selected one); stale f
         //    values of cells relaxed this step are upper bounds and the fresh keys are merged below
-        const uint32_t open_r = sOpenRow[r] & ~cbit;
+        const uint32_t open_r = (kBwd && solved) ? sOpenRow[r] : (sOpenRow[r] & ~cbit);
         const float frs = sF[ind - c + lane];
         const uint32_t rs_key = ((open_r >> lane) & 1u) ? fkey(frs) : kKeyInf;
         // -- closed/open update of the selected cell (:222-225) ------------------------------
@@ -188,6 +286,7 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
             closed |= cbit;
             if (!solved) open &= ~cbit;                     // the goal stays open once selected
             rm_key = kKeyInf;                               // this row's minimum is rebuilt below
+            if (kBwd && !solved) sV[ind] = 0.f;             // left the open set: no softmax weight
         }
         // -- expansion: rows r-1..r+1, columns c-1..c+1 (:228-249), branch-free ---------------
         uint32_t win = (c == 0) ? 3u : (7u << (c - 1));
@@ -217,13 +316,14 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
                 sG[rowbase + x] = g2;                        // :238
                 sF[rowbase + x] = fn;
                 sPar[rowbase + x] = uint16_t(ind);           // :246-249
+                if (kBwd) sV[rowbase + x] = expf(__fdiv_rn(-fn, a.sqrt_w));   // :207
             }
             open |= upd ? bit : 0u;                          // :242
             const bool better = upd & ((key < rm_key) | ((key == rm_key) & (x < rm_col)));
             rm_key = better ? key : rm_key;
             rm_col = better ? x : rm_col;
         }
-        if (solved) { t_solve = t; break; }                 // :251-252 (per-map early exit, App. A.4)
+        if (!kBwd && solved) { t_solve = t; break; }        // :251-252 (per-map early exit, App. A.4)
         if (near) sOpenRow[lane] = open;
         // -- fold the rescan into lane r's cached minimum -------------------------------------
         const uint32_t mr = __reduce_min_sync(kFull, rs_key);
@@ -234,6 +334,27 @@ __global__ void __launch_bounds__(32) astar_fwd_warp32_kernel(const nastar_fwd_p
         __syncwarp();
     }
     __syncwarp();
+
+    if (kBwd) {
+        // dL/dcost = -(1-g_ratio)/sqrt(W) * acc   (h = heuristic + cost, f = g_ratio*g + (1-g_ratio)*h)
+        const float coef = -omg / a.sqrt_w;
+        float* gOut = a.grad_cost + int64_t(b) * N;
+        const bool vec = ((N & 3) == 0) && aligned16(gOut);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i0 = 4 * (lane + 32 * j);
+            if (vec) {
+                if (i0 < N)
+                    *reinterpret_cast<float4*>(gOut + i0) = make_float4(coef * acc[4 * j], coef * acc[4 * j + 1],
+                                                                        coef * acc[4 * j + 2], coef * acc[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e < N) gOut[i0 + e] = coef * acc[4 * j + e];
+            }
+        }
+        return;
+    }
 
     // ---------------- backtrack (differentiable_astar.py:96-125, App. A.3) ------------------
     uint32_t path = 0u;

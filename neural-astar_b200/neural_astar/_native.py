@@ -51,7 +51,7 @@ class BwdParams(ctypes.Structure):
         ("obst", ctypes.c_void_p), ("obst_stride", ctypes.c_int64),
         ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
         ("g_ratio", ctypes.c_float), ("one_minus_g_ratio", ctypes.c_float), ("sqrt_w", ctypes.c_float),
-        ("T_batch", ctypes.c_void_p),
+        ("T_batch", ctypes.c_void_p), ("t_solve", ctypes.c_void_p),
         ("grad_histories", ctypes.c_void_p), ("grad_stride", ctypes.c_int64),
         ("grad_cost", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
@@ -205,7 +205,8 @@ def batch_steps(t_solve: torch.Tensor, n_steps: torch.Tensor, T: int) -> torch.T
     return out
 
 
-def backward(cost, start, goal, obst, grad_hist: torch.Tensor, T_batch: torch.Tensor, g_ratio: float) -> torch.Tensor:
+def backward(cost, start, goal, obst, grad_hist: torch.Tensor, T_batch: torch.Tensor, t_solve: torch.Tensor,
+             g_ratio: float) -> torch.Tensor:
     """dL/dcost [B,1,H,W] from dL/dhistories (closed form of the reference's autograd)."""
     L = lib()
     dev = cost.device
@@ -225,6 +226,7 @@ def backward(cost, start, goal, obst, grad_hist: torch.Tensor, T_batch: torch.Te
     p.B, p.H, p.W = B, H, W
     p.g_ratio, p.one_minus_g_ratio, p.sqrt_w = gr, omg, sq
     p.T_batch = T_batch.data_ptr()
+    p.t_solve = t_solve.data_ptr()
     with torch.cuda.device(dev):
         grad_cost = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
         ws_bytes = L.nastar_b200_backward_workspace_bytes(B, H, W)

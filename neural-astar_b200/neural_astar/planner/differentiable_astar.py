@@ -65,7 +65,7 @@ class _AstarSearch(torch.autograd.Function):
         grad_cost = None
         if ctx.needs_input_grad[0]:
             T_batch = _native.batch_steps(t_solve, n_steps, ctx.T)
-            grad_cost = _native.backward(cost, start, goal, obst, grad_hist.contiguous(), T_batch, ctx.g_ratio)
+            grad_cost = _native.backward(cost, start, goal, obst, grad_hist.contiguous(), T_batch, t_solve, ctx.g_ratio)
             if grad_cost.shape != cost.shape:  # cost had extra channels: only channel 0 is searched (:177)
                 full = torch.zeros_like(cost)
                 full[:, :1] = grad_cost
