@@ -181,18 +181,32 @@ int nastar_oracle_forward_literal(const float *cost, const float *start, const f
         memcpy(m->open, start + (size_t)b * N, sizeof(float) * N);       /* :187 */
         for (int i = 0; i < N; ++i) m->parents[i] = (float)m->goal;      /* :195-198 */
     }
-    int t = 0, last_t = 0;
-    for (t = 0; t < T; ++t) {
-        int any_unsolved = 0;
-#pragma omp parallel for schedule(static) reduction(| : any_unsolved)
-        for (int b = 0; b < B; ++b) {
-            any_unsolved |= literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N,
-                                         goal + (size_t)b * N, H, W, g_ratio, one_minus_g_ratio,
-                                         sqrt_w, t, trace ? trace + (size_t)b * T + t : NULL);
+    /* The reference runs one loop over t for the whole batch and stops when every map is solved
+     * (:251-252).  Maps only interact through that stop condition, so the same result is obtained
+     * without a barrier per step: phase 1 runs each map to its own solve step, T_batch is the
+     * maximum, phase 2 replays the post-solve iterations each map would still have executed. */
+    int32_t *done = (int32_t *)calloc((size_t)B, sizeof(int32_t));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < B; ++b) {
+        int t = 0;
+        for (t = 0; t < T; ++t) {
+            int uns = literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N, goal + (size_t)b * N,
+                                   H, W, g_ratio, one_minus_g_ratio, sqrt_w, t,
+                                   trace ? trace + (size_t)b * T + t : NULL);
+            if (!uns) { ++t; break; }
         }
-        last_t = t;
-        if (!any_unsolved) break;                           /* :251-252 */
+        done[b] = t; /* iterations executed so far */
     }
+    int tb = 0;
+    for (int b = 0; b < B; ++b) if (done[b] > tb) tb = done[b];
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < B; ++b) {
+        for (int t = done[b]; t < tb; ++t)
+            literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N, goal + (size_t)b * N, H, W,
+                         g_ratio, one_minus_g_ratio, sqrt_w, t, trace ? trace + (size_t)b * T + t : NULL);
+    }
+    free(done);
+    const int last_t = tb - 1;
     for (int b = 0; b < B; ++b) {
         memcpy(hist + (size_t)b * N, maps[b].hist, sizeof(float) * N);
         backtrack_literal(maps[b].parents, maps[b].goal, N, last_t, paths + (size_t)b * N); /* :255 */

@@ -1,0 +1,247 @@
+"""CPU-only tests: C-ABI surface, host-side module logic, sharding (incl. world_size-2 gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nastar_b200.h")
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "neural-astar_b200"), "-s", "all"])
+    from neural_astar import _native
+
+    return _native
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nastar_b200_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    """The shared library loads without a GPU and exports exactly what include/nastar_b200.h declares."""
+    lib = ctypes.CDLL(built_lib.LIB_PATH)
+    declared = _declared_functions()
+    assert len(declared) >= 9
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(built_lib.EXPORTS) == declared
+    lib.nastar_b200_abi_version.restype = ctypes.c_int
+    assert lib.nastar_b200_abi_version() == built_lib.ABI_VERSION
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C11 and carries no torch/CUDA types."""
+    c = tmp_path / "t.c"
+    c.write_text('#include "nastar_b200.h"\nint main(void){ nastar_fwd_params p; (void)p; '
+                 'return sizeof(nastar_bwd_params) > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(c), "-o", str(tmp_path / "t.o")])
+    code = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    assert "torch" not in code and "cudaStream_t" not in code and "#include <cuda" not in code
+
+
+def test_struct_layout_matches_ctypes(built_lib, tmp_path):
+    """ctypes mirrors of the parameter structs have the C compiler's size and field offsets."""
+    c = tmp_path / "sz.c"
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nastar_b200.h"\nint main(void){'
+                 'printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(nastar_fwd_params), offsetof(nastar_fwd_params, T),'
+                 'offsetof(nastar_fwd_params, workspace_bytes), sizeof(nastar_bwd_params),'
+                 'offsetof(nastar_bwd_params, t_solve), offsetof(nastar_bwd_params, grad_cost)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    F, Bw = built_lib.FwdParams, built_lib.BwdParams
+    want = [ctypes.sizeof(F), F.T.offset, F.workspace_bytes.offset, ctypes.sizeof(Bw), Bw.t_solve.offset,
+            Bw.grad_cost.offset]
+    assert got == want
+
+
+def test_engine_dispatch_and_workspace(built_lib):
+    L = built_lib.lib()
+    assert L.nastar_b200_engine_for(32, 32) == 1 and L.nastar_b200_engine_for(12, 12) == 1
+    assert L.nastar_b200_engine_for(64, 64) == 2 and L.nastar_b200_engine_for(64, 128) == 2
+    assert L.nastar_b200_engine_for(128, 128) == 2
+    assert L.nastar_b200_engine_for(256, 256) == 3
+    assert L.nastar_b200_engine_for(0, 5) == 0 and L.nastar_b200_engine_for(100000, 100000) == 0
+    assert L.nastar_b200_forward_workspace_bytes(8, 32, 32) == 0
+    assert L.nastar_b200_forward_workspace_bytes(4, 256, 256) >= 4 * 256 * 256 * 9
+    assert L.nastar_b200_status_string(2).decode().startswith("unsupported")
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu(built_lib):
+    L = built_lib.lib()
+    p = built_lib.FwdParams()
+    assert L.nastar_b200_forward(ctypes.byref(p), None) == 1  # NASTAR_EINVAL: null planes
+    assert L.nastar_b200_forward(None, None) == 1
+    assert L.nastar_b200_backward(None, None) == 1
+
+
+def test_no_cpu_fallback(built_lib):
+    """CPU tensors are refused loudly; the product never routes through the oracle or eager PyTorch."""
+    from neural_astar.planner import VanillaAstar
+
+    x = torch.ones(2, 1, 8, 8)
+    s = torch.zeros(2, 1, 8, 8)
+    s[:, :, 0, 0] = 1
+    g = torch.zeros(2, 1, 8, 8)
+    g[:, :, -1, -1] = 1
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        VanillaAstar()(x, s, g)
+    pkg = os.path.join(ROOT, "neural-astar_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().lower(), f"{f} mentions the oracle"
+
+
+def test_missing_library_fails_loudly(built_lib, monkeypatch, tmp_path):
+    from neural_astar import _native
+
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_native.NativeLibraryMissing):
+        _native.lib()
+
+
+def test_module_surface_matches_reference():
+    """Constructor signatures, attributes and state-dict keys of the reference."""
+    import inspect
+
+    from neural_astar.planner import NeuralAstar, VanillaAstar
+    from neural_astar.planner.differentiable_astar import AstarOutput, DifferentiableAstar, get_heuristic
+
+    assert list(inspect.signature(DifferentiableAstar.__init__).parameters)[1:] == ["g_ratio", "Tmax"]
+    assert list(inspect.signature(DifferentiableAstar.forward).parameters)[1:] == [
+        "cost_maps", "start_maps", "goal_maps", "obstacles_maps", "store_intermediate_results"]
+    assert list(inspect.signature(VanillaAstar.__init__).parameters)[1:] == ["g_ratio", "use_differentiable_astar"]
+    assert list(inspect.signature(NeuralAstar.__init__).parameters)[1:] == [
+        "g_ratio", "Tmax", "encoder_input", "encoder_arch", "encoder_depth", "learn_obstacles", "const",
+        "use_differentiable_astar"]
+    assert AstarOutput._fields == ("histories", "paths", "intermediate_results")
+    na = NeuralAstar()
+    keys = set(na.state_dict().keys())
+    assert "astar.neighbor_filter" in keys and "encoder.model.0.weight" in keys
+    assert "encoder.model.13.running_var" in keys
+    nf = na.astar.neighbor_filter
+    assert nf.shape == (1, 1, 3, 3) and not nf.requires_grad and float(nf.sum()) == 8 and float(nf[0, 0, 1, 1]) == 0
+    assert na.astar.get_heuristic is get_heuristic
+    with pytest.raises(AssertionError):
+        DifferentiableAstar(Tmax=0.0)
+    d = DifferentiableAstar(Tmax=0.25)
+    assert d.train().num_steps(32) == 256 and d.eval().num_steps(32) == 1024  # differentiable_astar.py:200-202
+    with pytest.raises(AssertionError):
+        d(torch.ones(8, 8), torch.ones(8, 8), torch.ones(8, 8), torch.ones(8, 8))  # ndim asserts (:172-175)
+    wc = NeuralAstar(encoder_input="rgb+", encoder_arch="CNNDownSize", encoder_depth=3, const=10.0)
+    assert wc.encoder.const.item() == 10.0
+
+
+def test_reference_checkpoint_loads_with_all_keys_matched():
+    from neural_astar.planner import NeuralAstar
+
+    state = np.load(os.path.join(ROOT, "tests", "golden", "mazes032_ckpt_planner_state.npz"))
+    msg = NeuralAstar(encoder_arch="CNN").load_state_dict({k: torch.from_numpy(state[k]) for k in state.files})
+    assert str(msg) == "<All keys matched successfully>"
+
+
+def test_encoder_matches_reference_cost_maps():
+    """The re-provided CNN encoder reproduces the reference encoder's cost maps on CPU (golden fixture)."""
+    from golden_util import Golden
+    from neural_astar.planner import NeuralAstar
+
+    g = Golden("mazes032_neural_test")
+    state = np.load(os.path.join(ROOT, "tests", "golden", "mazes032_ckpt_planner_state.npz"))
+    planner = NeuralAstar(encoder_arch="CNN")
+    planner.load_state_dict({k: torch.from_numpy(state[k]) for k in state.files})
+    planner.eval()
+    with torch.no_grad():
+        cost = planner.encode(torch.from_numpy(g.obst[:8]), torch.from_numpy(g.start[:8]),
+                              torch.from_numpy(g.goal[:8]))
+    np.testing.assert_allclose(cost.numpy(), g.cost[:8], rtol=1e-5, atol=1e-6)
+    # CNNDownSize geometry of the WarCraft config (96x96 RGB -> 12x12 costs, encoder.py:81-97)
+    wc = NeuralAstar(encoder_input="rgb+", encoder_arch="CNNDownSize", encoder_depth=3, learn_obstacles=True,
+                     const=10.0).eval()
+    s = torch.zeros(2, 1, 12, 12)
+    s[:, :, 0, 0] = 1
+    with torch.no_grad():
+        c = wc.encode(torch.rand(2, 3, 96, 96), s, s.flip(-1, -2))
+    assert c.shape == (2, 1, 12, 12) and float(c.min()) >= 0 and float(c.max()) <= 10
+
+
+def test_get_heuristic_matches_formula():
+    from neural_astar.planner.differentiable_astar import get_heuristic
+
+    goal = torch.zeros(2, 5, 7)
+    goal[0, 4, 6] = 1
+    goal[1, 0, 3] = 1
+    h = get_heuristic(goal).numpy()
+    for b, (gy, gx) in enumerate(((4, 6), (0, 3))):
+        for y in range(5):
+            for x in range(7):
+                dy, dx = abs(y - gy), abs(x - gx)
+                want = np.float32(np.float32(dy + dx - min(dy, dx)) +
+                                  np.float32(0.001) * np.sqrt(np.float32(dy * dy + dx * dx)))
+                assert h[b, y, x] == pytest.approx(float(want), abs=1e-6)
+
+
+@pytest.mark.parametrize("n,world", [(100, 1), (100, 2), (100, 8), (13, 4), (3, 8), (0, 2), (8192, 8)])
+def test_shard_range_partitions_the_batch(n, world):
+    from neural_astar.utils.distributed import shard_range
+
+    spans = [shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [e - b for b, e in spans]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from neural_astar.utils.distributed import aggregate_throughput, shard_batch
+
+    full = torch.arange(101 * 4).reshape(101, 1, 2, 2).float()
+    (mine,) = shard_batch((full,), rank, world)
+    maps, exp, sec = aggregate_throughput(mine.shape[0], float(mine.sum()), 1.0 + rank)
+    q.put((rank, mine.shape[0], maps, exp, sec, float(mine[0].sum())))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo():
+    """world_size-2 run on CPU: shards are disjoint, cover the batch, and throughput aggregates as
+    (SUM maps, SUM expansions, MAX seconds)."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full_sum = float(torch.arange(101 * 4).sum())
+    assert [r[1] for r in res] == [51, 50]
+    for r in res:
+        assert r[2] == 101 and r[3] == full_sum and r[4] == 2.0
+    assert res[0][5] == float(torch.arange(4).sum())
+    assert res[1][5] == float(torch.arange(51 * 4, 51 * 4 + 4).sum())
