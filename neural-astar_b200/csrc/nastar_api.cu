@@ -6,7 +6,7 @@
 
 #include "../../include/nastar_b200.h"
 #include "nastar_fwd_generic.cuh"
-#include "nastar_fwd_warp32.cuh"
+#include "nastar_warp32.cuh"
 
 namespace {
 std::atomic<uint64_t> g_launches{0};
@@ -95,13 +95,12 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         if (e != cudaSuccess) return cuda_fail(e);
     }
     if (engine == 1) {
-        const size_t smem = nastar::Warp32Smem::bytes(N);
         nastar::W32Args a{};
         a.f = *p;
         if (p->trace)
-            nastar::astar_warp32_kernel<true, false><<<p->B, 32, smem, stream>>>(a);
+            nastar::astar_warp32_kernel<true, false><<<p->B, 32, 0, stream>>>(a);
         else
-            nastar::astar_warp32_kernel<false, false><<<p->B, 32, smem, stream>>>(a);
+            nastar::astar_warp32_kernel<false, false><<<p->B, 32, 0, stream>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
         const nastar::GenericLayout L(p->H, p->W);
@@ -137,7 +136,6 @@ int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int engine = nastar_b200_engine_for(p->H, p->W);
     if (engine != 1) return NASTAR_EUNSUPPORTED;   // training configs of the reference are 32x32 / 12x12
-    const int N = p->H * p->W;
     nastar::W32Args a{};
     a.f.cost = p->cost;   a.f.cost_stride = p->cost_stride;
     a.f.start = p->start; a.f.start_stride = p->start_stride;
@@ -153,8 +151,8 @@ int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
     a.grad_hist = p->grad_histories;
     a.grad_stride = p->grad_stride;
     a.grad_cost = p->grad_cost;
-    const size_t smem = nastar::Warp32Smem::bytes(N, true);
-    nastar::astar_warp32_kernel<false, true><<<p->B, 32, smem, stream>>>(a);
+    // dynamic shared memory = the dense softmax-numerator plane v (padded 32x32 fp32)
+    nastar::astar_warp32_kernel<false, true><<<p->B, 32, nastar::kCells * sizeof(float), stream>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);

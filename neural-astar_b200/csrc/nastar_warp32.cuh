@@ -1,0 +1,374 @@
+// nastar_warp32.cuh — warp-resident engine for maps with H <= 32 and W <= 32 (forward + backward).
+//
+// Replaces the T-step loop + backtrack of DifferentiableAstar.forward
+// (/root/reference/src/neural_astar/planner/differentiable_astar.py:187-255) and the autograd
+// through it, one map per warp.  Design (DESIGN.md "warp32 engine"):
+//   * the map lives in shared memory in a PADDED 32x32 layout (cell id rc = y*32 + x), so every
+//     index is a shift/mask and every plane sits at a compile-time offset;
+//   * lane y owns grid row y: passable / open / closed rows are 32-bit masks in registers, and
+//     the lane caches its row's best open cell (order-preserving f key, column);
+//   * node selection (:206-209; softmax+argmax == arg-min of (f, flat index))
+//     is two REDUX.MINs over the 32 cached row minima: min key, then min (row<<5|col) among ties;
+//   * expansion (:228-249) touches <= 8 cells in rows r-1..r+1: those three lanes relax their
+//     <= 3 cells with branch-free mask algebra and fold the new keys into their cached minimum —
+//     insertions/decreases never need a rescan;
+//   * only row r lost its minimum (the selected cell): all 32 lanes rescan that one row (one
+//     conflict-free LDS + two REDUX.MINs), overlapped with the expansion's dependency chain;
+//   * planes are staged with 1-D TMA bulk copies (cp.async.bulk + mbarrier) when W == 32 and
+//     results leave as coalesced 128-bit stores; the loop itself never touches HBM.
+//   kBwd = true replays the same state machine and accumulates the closed-form gradient of the
+//   straight-through softmax — same code path, so the replay cannot drift.
+#pragma once
+#include "../../include/nastar_b200.h"
+#include "nastar_common.cuh"
+
+namespace nastar {
+
+// Kernel arguments: the forward parameters plus the extra fields of nastar_bwd_params.
+struct W32Args {
+    nastar_fwd_params f;
+    // backward only
+    float sqrt_w;
+    const int32_t* T_batch;     // device scalar: loop iterations the reference would execute
+    const int32_t* t_solve_in;  // forward's t_solve[] (goal clamp blocking, App. B)
+    const float* grad_hist;
+    int64_t grad_stride;
+    float* grad_cost;
+};
+
+constexpr int kCells = 1024;  // padded 32 x 32
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+struct __align__(16) W32Smem {
+    float cost[kCells];        // staged cost plane (padded)
+    float f[kCells];           // f = g_ratio*g + (1-g_ratio)*h of opened cells
+    float2 ghbuf[kCells + 4];  // {g, h} per cell at ghbuf[2 + rc]; 2 guard cells on either side make the
+                               // c-1 / c+1 window loads of the first/last cell addressable (16-B aligned body)
+    uint16_t par[kCells];      // parent cell id (padded rc) of opened cells
+    uint32_t open_row[32];     // every lane's open row, refreshed each step (rescan input)
+    uint32_t bits_a[32];       // closed rows for the epilogue
+    uint32_t bits_b[32];       // path rows for the epilogue
+    unsigned long long bar;    // mbarrier for the TMA prologue
+};
+
+template <bool kTrace, bool kBwd>
+__global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
+    __shared__ W32Smem S;
+    extern __shared__ __align__(16) float sV[];  // backward only: v = exp(-f/sqrt(W)) of open cells, else 0
+    const nastar_fwd_params& p = a.f;
+    float2* const sGH = S.ghbuf + 2;
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x;
+    const int H = p.H, W = p.W, N = H * W;
+
+    const float* gCost = p.cost + int64_t(b) * p.cost_stride;
+    const float* gStart = p.start + int64_t(b) * p.start_stride;
+    const float* gGoal = p.goal + int64_t(b) * p.goal_stride;
+    const float* gObst = p.obst + int64_t(b) * p.obst_stride;
+    const bool obst_is_cost = (gObst == gCost);
+
+    // ---------------- prologue: stage planes, build row masks ------------------------------
+    uint32_t pass = 0u;
+    int start_rc = -1, goal_rc = -1;
+    const bool tma = (W == 32) && aligned16(gCost) && aligned16(gStart) && aligned16(gGoal) && aligned16(gObst);
+    if (tma) {
+        // flat layout == padded layout: bulk-copy whole planes (start/goal/obstacles are parked in the
+        // f and {g,h} planes, which are not live yet)
+        float* tStart = S.f;
+        float* tGoal = reinterpret_cast<float*>(sGH);
+        float* tObst = tGoal + kCells;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = uint32_t(N) * 4u;
+            mbar_expect_tx(bar, bytes * (obst_is_cost ? 3u : 4u));
+            tma_load_1d(S.cost, gCost, bytes, bar);
+            tma_load_1d(tStart, gStart, bytes, bar);
+            tma_load_1d(tGoal, gGoal, bytes, bar);
+            if (!obst_is_cost) tma_load_1d(tObst, gObst, bytes, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+        const float* sObst = obst_is_cost ? S.cost : tObst;
+#pragma unroll 4
+        for (int y = 0; y < H; ++y) {
+            const int i = (y << 5) + lane;
+            const uint32_t wo = __ballot_sync(kFull, sObst[i] != 0.f);
+            const uint32_t ws = __ballot_sync(kFull, tStart[i] != 0.f);
+            const uint32_t wg = __ballot_sync(kFull, tGoal[i] != 0.f);
+            if (lane == y) pass = wo;
+            if (start_rc < 0 && ws) start_rc = (y << 5) + __ffs(ws) - 1;
+            if (goal_rc < 0 && wg) goal_rc = (y << 5) + __ffs(wg) - 1;
+        }
+    } else {
+        const bool in = lane < W;
+#pragma unroll 4
+        for (int y = 0; y < H; ++y) {
+            const int i = y * W + lane;
+            const float vc = in ? __ldg(gCost + i) : 0.f;
+            const float vo = obst_is_cost ? vc : (in ? __ldg(gObst + i) : 0.f);
+            const float vs = in ? __ldg(gStart + i) : 0.f;
+            const float vg = in ? __ldg(gGoal + i) : 0.f;
+            S.cost[(y << 5) + lane] = vc;
+            const uint32_t wo = __ballot_sync(kFull, vo != 0.f);
+            const uint32_t ws = __ballot_sync(kFull, vs != 0.f);
+            const uint32_t wg = __ballot_sync(kFull, vg != 0.f);
+            if (lane == y) pass = wo;
+            if (start_rc < 0 && ws) start_rc = (y << 5) + __ffs(ws) - 1;
+            if (goal_rc < 0 && wg) goal_rc = (y << 5) + __ffs(wg) - 1;
+        }
+    }
+    if (goal_rc < 0) goal_rc = 0;  // argmax of an all-zero plane (differentiable_astar.py:197)
+    const int gy = goal_rc >> 5, gx = goal_rc & 31;
+    __syncwarp();
+    // h = heuristic + cost (:191-192), one row per iteration; overwrites the parked planes
+#pragma unroll 4
+    for (int y = 0; y < H; ++y) {
+        const int i = (y << 5) + lane;
+        sGH[i] = make_float2(0.f, __fadd_rn(heuristic(y, lane, gy, gx), S.cost[i]));
+    }
+    __syncwarp();
+
+    const float gr = p.g_ratio, omg = p.one_minus_g_ratio;
+    uint32_t open = 0u, closed = 0u;
+    uint32_t rm_key = kKeyInf;
+    int rm_col = 0;
+
+    float Gh[32], acc[32];  // backward: upstream gradient / accumulator of cell 4*(lane+32j)+e (padded id)
+    int Tb = 0, ts_in = NASTAR_TS_CAPPED;
+    if (kBwd) {
+        float4* sV4 = reinterpret_cast<float4*>(sV);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sV4[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        Tb = *a.T_batch;
+        ts_in = a.t_solve_in[b];
+        const float* gG = a.grad_hist + int64_t(b) * a.grad_stride;
+        const bool vec = (W == 32) && aligned16(gG);
+        // clamp(hist + sel) blocks the gradient at a goal that is re-selected after its solve step
+        // (pre-clamp value 2, differentiable_astar.py:222-223)
+        const bool blocked = (ts_in >= 0) && (ts_in < Tb - 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p0 = 4 * (lane + 32 * j);
+            const int y = p0 >> 5, x0 = p0 & 31;
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec) {
+                if (y < H) g4 = __ldg(reinterpret_cast<const float4*>(gG + p0));
+            } else if (y < H) {
+                if (x0 + 0 < W) g4.x = __ldg(gG + y * W + x0 + 0);
+                if (x0 + 1 < W) g4.y = __ldg(gG + y * W + x0 + 1);
+                if (x0 + 2 < W) g4.z = __ldg(gG + y * W + x0 + 2);
+                if (x0 + 3 < W) g4.w = __ldg(gG + y * W + x0 + 3);
+            }
+            Gh[4 * j + 0] = (blocked && p0 + 0 == goal_rc) ? 0.f : g4.x;
+            Gh[4 * j + 1] = (blocked && p0 + 1 == goal_rc) ? 0.f : g4.y;
+            Gh[4 * j + 2] = (blocked && p0 + 2 == goal_rc) ? 0.f : g4.z;
+            Gh[4 * j + 3] = (blocked && p0 + 3 == goal_rc) ? 0.f : g4.w;
+            acc[4 * j + 0] = acc[4 * j + 1] = acc[4 * j + 2] = acc[4 * j + 3] = 0.f;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) S.par[goal_rc] = uint16_t(goal_rc);  // parents initialised to the goal (:195-198)
+    if (start_rc >= 0) {
+        const float f0 = f_value(gr, omg, 0.f, sGH[start_rc].y);
+        if (lane == 0) {
+            S.par[start_rc] = uint16_t(goal_rc);
+            S.f[start_rc] = f0;                      // g = 0 already (:193)
+            if (kBwd) sV[start_rc] = expf(__fdiv_rn(-f0, a.sqrt_w));  // :207
+        }
+        if (lane == (start_rc >> 5)) {
+            open = 1u << (start_rc & 31);            // open_maps = start_maps (:187)
+            rm_key = fkey(f0);
+            rm_col = start_rc & 31;
+        }
+    }
+    S.open_row[lane] = open;
+    __syncwarp();
+
+    // ---------------- the search loop (differentiable_astar.py:203-252) --------------------
+    const int T = kBwd ? Tb : p.T;
+    // post-solve steps are stationary when g_ratio >= 0.5 (the goal keeps being re-selected and
+    // nothing changes): the backward then adds them in one go
+    const bool stationary_ok = (gr >= 0.5f);
+    int t_solve = NASTAR_TS_CAPPED;
+    int steps = 0;
+    int32_t* trace = kTrace ? (p.trace + int64_t(b) * p.T) : nullptr;
+    const float2* ghrow = sGH + (lane << 5);      // this lane's row of {g,h}
+    for (int t = 0; t < T; ++t) {
+        // -- select: lexicographic arg-min of (f key, row, col) with two REDUX.MINs -----------
+        const uint32_t m = __reduce_min_sync(kFull, rm_key);
+        if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
+        if (kBwd) {
+            // y_t = v / sum(v) over the open set at the START of step t; accumulate
+            // y_t[p] * (Gh[p] - <Gh, y_t>)  (times the number of identical post-solve steps)
+            const float4* sV4 = reinterpret_cast<const float4*>(sV);
+            float4 v[8];
+            float s_ = 0.f, d_ = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = sV4[lane + 32 * j];
+                s_ += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+                d_ = fmaf(Gh[4 * j + 0], v[j].x, d_);
+                d_ = fmaf(Gh[4 * j + 1], v[j].y, d_);
+                d_ = fmaf(Gh[4 * j + 2], v[j].z, d_);
+                d_ = fmaf(Gh[4 * j + 3], v[j].w, d_);
+            }
+            s_ = warp_sum(s_);
+            d_ = warp_sum(d_);
+            const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
+            const float wgt = last ? float(Tb - t) : 1.f;
+            const float inv = wgt / s_;
+            const float dd = d_ / s_;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[4 * j + 0] = fmaf(v[j].x * inv, Gh[4 * j + 0] - dd, acc[4 * j + 0]);
+                acc[4 * j + 1] = fmaf(v[j].y * inv, Gh[4 * j + 1] - dd, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(v[j].z * inv, Gh[4 * j + 2] - dd, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(v[j].w * inv, Gh[4 * j + 3] - dd, acc[4 * j + 3]);
+            }
+            if (last) break;
+        }
+        const uint32_t ind = __reduce_min_sync(kFull, (rm_key == m) ? uint32_t((lane << 5) | rm_col) : 0xFFFFFFFFu);
+        const int r = int(ind >> 5), c = int(ind & 31u);
+        steps = t + 1;
+        if (kTrace && lane == 0) trace[t] = r * W + c;
+        const bool solved = (int(ind) == goal_rc);          // :219-220
+        const uint32_t m1 = 1u << c;                        // column masks of the 3-wide window;
+        const uint32_t m0 = m1 >> 1, m2 = m1 << 1;          // they fall off the row at c == 0 / 31
+        // -- rescan inputs for row r (pre-expansion open cells minus the selected one); stale f
+        //    values of cells relaxed this step are upper bounds and the fresh keys are merged below
+        const uint32_t open_r = (kBwd && solved) ? S.open_row[r] : (S.open_row[r] & ~m1);
+        const float frs = S.f[(r << 5) + lane];
+        const uint32_t rs_key = ((open_r >> lane) & 1u) ? fkey(frs) : kKeyInf;
+        // -- expansion inputs ----------------------------------------------------------------
+        const int dr = lane - r;
+        const bool isr = (dr == 0);
+        const bool near = (unsigned(dr + 1) <= 2u);
+        // only the three row lanes load (rows are 256 B apart = same banks; 32 lanes would serialise)
+        float2 n0 = make_float2(0.f, 0.f), n1 = n0, n2 = n0;
+        if (near) { n0 = ghrow[c - 1]; n1 = ghrow[c]; n2 = ghrow[c + 1]; }   // guard cells make c-1/c+1 safe
+        const float g2 = __fadd_rn(sGH[ind].x, S.cost[ind]);               // :234, cost of the SELECTED node
+        // -- closed/open update of the selected cell (:222-225) ------------------------------
+        if (isr) {
+            closed |= m1;
+            if (!solved) open &= ~m1;                       // the goal stays open once selected
+            rm_key = kKeyInf;                               // this row's minimum is rebuilt below
+            if (kBwd && !solved) sV[ind] = 0.f;             // left the open set: no softmax weight
+        }
+        // -- expansion (:228-249) as mask algebra on this lane's row ---------------------------
+        //    idx = ((1-open)(1-hist) + open*(g > g2)) * neighbours * obstacles   (:235-236)
+        const uint32_t win = isr ? (m0 | m2) : (m0 | m1 | m2);
+        const uint32_t cand = near ? (win & pass) : 0u;
+        const uint32_t gt = ((n0.x > g2) ? m0 : 0u) | ((n1.x > g2) ? m1 : 0u) | ((n2.x > g2) ? m2 : 0u);
+        const uint32_t upd = cand & ((open & gt) | ~(open | closed));
+        open |= upd;                                        // :242
+        const float ag = __fmul_rn(gr, g2);
+        const float f0n = __fadd_rn(ag, __fmul_rn(omg, n0.y));
+        const float f1n = __fadd_rn(ag, __fmul_rn(omg, n1.y));
+        const float f2n = __fadd_rn(ag, __fmul_rn(omg, n2.y));
+        const bool u0 = (upd & m0) != 0u, u1 = (upd & m1) != 0u, u2 = (upd & m2) != 0u;
+        const int cell = (lane << 5) + c;
+        if (u0) { sGH[cell - 1].x = g2; S.f[cell - 1] = f0n; S.par[cell - 1] = uint16_t(ind); }   // :238, :246-249
+        if (u1) { sGH[cell].x = g2;     S.f[cell] = f1n;     S.par[cell] = uint16_t(ind); }
+        if (u2) { sGH[cell + 1].x = g2; S.f[cell + 1] = f2n; S.par[cell + 1] = uint16_t(ind); }
+        if (kBwd) {
+            if (u0) sV[cell - 1] = expf(__fdiv_rn(-f0n, a.sqrt_w));   // :207
+            if (u1) sV[cell] = expf(__fdiv_rn(-f1n, a.sqrt_w));
+            if (u2) sV[cell + 1] = expf(__fdiv_rn(-f2n, a.sqrt_w));
+        }
+        // fold the fresh keys (ascending column, strict < keeps the lowest column on ties)
+        const uint32_t k0 = u0 ? fkey(f0n) : kKeyInf, k1 = u1 ? fkey(f1n) : kKeyInf, k2 = u2 ? fkey(f2n) : kKeyInf;
+        uint32_t bk = k0;
+        int bc = c - 1;
+        if (k1 < bk) { bk = k1; bc = c; }
+        if (k2 < bk) { bk = k2; bc = c + 1; }
+        if ((bk < rm_key) | ((bk == rm_key) & (bc < rm_col))) { rm_key = bk; rm_col = bc; }
+        if (!kBwd && solved) { t_solve = t; break; }        // :251-252 (per-map early exit, App. A.4)
+        if (near) S.open_row[lane] = open;
+        // -- fold the rescan into lane r's cached minimum -------------------------------------
+        const uint32_t mr = __reduce_min_sync(kFull, rs_key);
+        const uint32_t mc = __reduce_min_sync(kFull, (rs_key == mr) ? uint32_t(lane) : 0xFFFFFFFFu);
+        const bool take = isr & ((mr < rm_key) | ((mr == rm_key) & (int(mc) < rm_col)));
+        rm_key = take ? mr : rm_key;
+        rm_col = take ? int(mc) : rm_col;
+        __syncwarp();
+    }
+    __syncwarp();
+
+    if (kBwd) {
+        // dL/dcost = -(1-g_ratio)/sqrt(W) * acc   (h = heuristic + cost, f = g_ratio*g + (1-g_ratio)*h)
+        const float coef = -omg / a.sqrt_w;
+        float* gOut = a.grad_cost + int64_t(b) * N;
+        const bool vec = (W == 32) && aligned16(gOut);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int p0 = 4 * (lane + 32 * j);
+            const int y = p0 >> 5, x0 = p0 & 31;
+            if (y < H) {
+                if (vec) {
+                    *reinterpret_cast<float4*>(gOut + p0) =
+                        make_float4(coef * acc[4 * j], coef * acc[4 * j + 1], coef * acc[4 * j + 2], coef * acc[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (x0 + e < W) gOut[y * W + x0 + e] = coef * acc[4 * j + e];
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- backtrack (differentiable_astar.py:96-125, App. A.3) ------------------
+    uint32_t path = 0u;
+    {
+        if (lane == gy) path |= 1u << gx;
+        int loc = S.par[goal_rc];
+        const int hops = (t_solve >= 0) ? N : (p.T - 1);
+        for (int k = 0; k < hops; ++k) {
+            if (lane == (loc >> 5)) path |= 1u << (loc & 31);
+            if (loc == start_rc || loc == goal_rc) break;   // reached the start (or a self-loop)
+            loc = S.par[loc];
+        }
+    }
+
+    // ---------------- epilogue: coalesced stores of histories / paths -----------------------
+    S.bits_a[lane] = closed;
+    S.bits_b[lane] = path;
+    __syncwarp();
+    float* gHist = p.histories + int64_t(b) * N;
+    long long* gPath = reinterpret_cast<long long*>(p.paths) + int64_t(b) * N;
+    if (W == 32 && aligned16(gHist) && aligned16(gPath)) {
+        const int x = (lane & 7) << 2;
+#pragma unroll 4
+        for (int j = 0; j < 8; ++j) {
+            const int y = (lane >> 3) + 4 * j;
+            if (y < H) {
+                const int i4 = lane + 32 * j;
+                const uint32_t cb = S.bits_a[y] >> x, pb = S.bits_b[y] >> x;
+                reinterpret_cast<float4*>(gHist)[i4] = make_float4((cb & 1u) ? 1.f : 0.f, (cb & 2u) ? 1.f : 0.f,
+                                                                   (cb & 4u) ? 1.f : 0.f, (cb & 8u) ? 1.f : 0.f);
+                reinterpret_cast<longlong2*>(gPath)[2 * i4] = make_longlong2((pb & 1u) ? 1ll : 0ll, (pb & 2u) ? 1ll : 0ll);
+                reinterpret_cast<longlong2*>(gPath)[2 * i4 + 1] = make_longlong2((pb & 4u) ? 1ll : 0ll, (pb & 8u) ? 1ll : 0ll);
+            }
+        }
+    } else {
+        for (int y = 0; y < H; ++y) {
+            if (lane < W) {
+                gHist[y * W + lane] = ((S.bits_a[y] >> lane) & 1u) ? 1.f : 0.f;
+                gPath[y * W + lane] = ((S.bits_b[y] >> lane) & 1u) ? 1ll : 0ll;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (p.t_solve) p.t_solve[b] = t_solve;
+        if (p.n_steps) p.n_steps[b] = steps;
+    }
+}
+
+}  // namespace nastar
