@@ -19,12 +19,63 @@ class EncoderBase(nn.Module):
         self.model = self.construct_encoder(input_dim, encoder_depth)
         # learnable scale when given (reference :25-28); plain 1.0 otherwise
         self.const = nn.Parameter(torch.ones(1) * const) if const is not None else 1.0
+        self._plan = None       # cached inference plan (folded weights) for the cuDNN fast path
+        self._plan_key = None
 
     def construct_encoder(self, input_dim: int, encoder_depth: int) -> nn.Module:
         raise NotImplementedError
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if (not self.training) and x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32:
+            plan = self._inference_plan(x.device)
+            if plan is not None:
+                return torch.sigmoid(_run_plan(plan, x)) * self.const
         return torch.sigmoid(self.model(x)) * self.const
+
+    # ---- eval-mode cuDNN fast path (encoder -> search hand-off) -----------------
+    # Still plain PyTorch/cuDNN: BatchNorm (running stats) is folded into the preceding conv, activations
+    # run channels-last (no NCHW<->NHWC transposes), and conv+bias+ReLU is one cuDNN fused op.  Same math
+    # as self.model(x) up to fp32 re-association of the BN scale; training / autograd use self.model.
+    def _inference_plan(self, device):
+        if not isinstance(self.model, nn.Sequential):
+            return None
+        tensors = [t for t in list(self.model.parameters()) + list(self.model.buffers())]
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
+        if key == self._plan_key:
+            return self._plan
+        mods = list(self.model)
+        plan, i = [], 0
+        while i < len(mods):
+            conv = mods[i]
+            if not (isinstance(conv, nn.Conv2d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d)
+                    and conv.groups == 1 and conv.bias is not None):
+                self._plan, self._plan_key = None, key
+                return None
+            bn = mods[i + 1]
+            i += 2
+            relu = i < len(mods) and isinstance(mods[i], nn.ReLU)
+            i += 1 if relu else 0
+            pool = mods[i] if i < len(mods) and isinstance(mods[i], nn.MaxPool2d) else None
+            i += 1 if pool is not None else 0
+            with torch.no_grad():
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+                b = ((conv.bias - bn.running_mean) * scale + bn.bias).contiguous()
+            plan.append((w, b, conv.stride, conv.padding, conv.dilation, relu, pool))
+        self._plan, self._plan_key = plan, key
+        return plan
+
+
+def _run_plan(plan, x: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous(memory_format=torch.channels_last)
+    for w, b, stride, padding, dilation, relu, pool in plan:
+        if relu:
+            x = torch.cudnn_convolution_relu(x, w, b, stride, padding, dilation, 1)
+        else:
+            x = torch.nn.functional.conv2d(x, w, b, stride, padding, dilation, 1)
+        if pool is not None:
+            x = pool(x)
+    return x
 
 
 def _conv_stack(widths: List[int], pool: bool) -> nn.Sequential:

@@ -152,3 +152,35 @@ def test_large_maps_vs_oracle(oracle, H, W, B):
         np.testing.assert_array_equal(ns.cpu().numpy(), ref.n_steps)
         np.testing.assert_array_equal(hist.cpu().numpy(), ref.histories)
         np.testing.assert_array_equal(paths.cpu().numpy(), ref.paths)
+
+
+@pytest.mark.parametrize("arch,inp,depth,const,shape", [("CNN", "m+", 4, None, (16, 1, 32, 32)),
+                                                         ("CNNDownSize", "rgb+", 3, 10.0, (8, 3, 96, 96))])
+def test_encoder_eval_fast_path_matches_module(arch, inp, depth, const, shape):
+    """Eval-mode cuDNN fast path (folded BN, channels-last, fused bias+ReLU) == nn.Sequential path up to TF32."""
+    from neural_astar.planner import NeuralAstar
+
+    torch.manual_seed(3)
+    na = NeuralAstar(encoder_input=inp, encoder_arch=arch, encoder_depth=depth, const=const,
+                     learn_obstacles=(arch != "CNN")).cuda()
+    # make BatchNorm statistics non-trivial
+    na.train()
+    x = torch.rand(shape, device="cuda")
+    hw = 32 if arch == "CNN" else 12
+    s = torch.zeros((shape[0], 1, hw, hw), device="cuda"); s[:, :, 0, 0] = 1
+    g = torch.zeros_like(s); g[:, :, -1, -1] = 1
+    for _ in range(3):
+        na.encode(x, s, g)
+    na.eval()
+    with torch.no_grad():
+        fast = na.encode(x, s, g)
+    assert na.encoder._plan is not None
+    slow = na.encode(x, s, g)           # grad enabled -> reference module path
+    assert slow.requires_grad and not fast.requires_grad
+    scale = 1.0 if const is None else const
+    assert float((fast - slow).abs().max()) < 3e-3 * scale
+    # plan is invalidated when weights change
+    with torch.no_grad():
+        na.encoder.model[0].weight.mul_(1.5)
+        fast2 = na.encode(x, s, g)
+    assert float((fast2 - fast).abs().max()) > 1e-4
