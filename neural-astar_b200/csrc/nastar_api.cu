@@ -5,7 +5,7 @@
 #include <cstdio>
 
 #include "../../include/nastar_b200.h"
-#include "nastar_fwd_generic.cuh"
+#include "nastar_generic.cuh"
 #include "nastar_warp32.cuh"
 
 namespace {
@@ -79,15 +79,15 @@ size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
 }
 
 size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
-    (void)B; (void)H; (void)W;
-    return 0;
+    const int e = nastar_b200_engine_for(H, W);
+    if (B <= 0 || e < 2) return 0;
+    return size_t(generic_slots(B)) * nastar::GenericLayout(H, W).slot_total(e == 3, true);
 }
 
 int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
     if (!p || !p->cost || !p->start || !p->goal || !p->obst || !p->histories || !p->paths) return NASTAR_EINVAL;
     if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->T < 1) return NASTAR_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    const int N = p->H * p->W;
     const int engine = nastar_b200_engine_for(p->H, p->W);
     if (engine == 0) return NASTAR_EUNSUPPORTED;
     if (p->trace) {
@@ -111,15 +111,17 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
             grid = generic_slots(p->B);
             if (!p->workspace || p->workspace_bytes < size_t(grid) * L.slot_bytes()) return NASTAR_EWORKSPACE;
         }
+        nastar::GenArgs ga{};
+        ga.f = *p;
         auto launch = [&](auto kernel) -> cudaError_t {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if (e != cudaSuccess) return e;
-            kernel<<<grid, 32, smem, stream>>>(*p);
+            kernel<<<grid, 32, smem, stream>>>(ga);
             return cudaSuccess;
         };
         cudaError_t e;
-        if (global) e = p->trace ? launch(nastar::astar_fwd_generic_kernel<true, true>) : launch(nastar::astar_fwd_generic_kernel<true, false>);
-        else e = p->trace ? launch(nastar::astar_fwd_generic_kernel<false, true>) : launch(nastar::astar_fwd_generic_kernel<false, false>);
+        if (global) e = p->trace ? launch(nastar::astar_generic_kernel<true, true, false>) : launch(nastar::astar_generic_kernel<true, false, false>);
+        else e = p->trace ? launch(nastar::astar_generic_kernel<false, true, false>) : launch(nastar::astar_generic_kernel<false, false, false>);
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
@@ -135,7 +137,43 @@ int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
     if (p->B <= 0 || p->H <= 0 || p->W <= 0) return NASTAR_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int engine = nastar_b200_engine_for(p->H, p->W);
-    if (engine != 1) return NASTAR_EUNSUPPORTED;   // training configs of the reference are 32x32 / 12x12
+    if (engine == 0) return NASTAR_EUNSUPPORTED;
+    if (engine >= 2) {
+        const nastar::GenericLayout L(p->H, p->W);
+        const bool global = (engine == 3);
+        const int grid = generic_slots(p->B);
+        if (!p->workspace || p->workspace_bytes < size_t(grid) * L.slot_total(global, true)) return NASTAR_EWORKSPACE;
+        nastar::GenArgs ga{};
+        ga.f.cost = p->cost;   ga.f.cost_stride = p->cost_stride;
+        ga.f.start = p->start; ga.f.start_stride = p->start_stride;
+        ga.f.goal = p->goal;   ga.f.goal_stride = p->goal_stride;
+        ga.f.obst = p->obst;   ga.f.obst_stride = p->obst_stride;
+        ga.f.B = p->B; ga.f.H = p->H; ga.f.W = p->W;
+        ga.f.g_ratio = p->g_ratio;
+        ga.f.one_minus_g_ratio = p->one_minus_g_ratio;
+        ga.f.workspace = p->workspace;
+        ga.f.workspace_bytes = p->workspace_bytes;
+        ga.sqrt_w = p->sqrt_w;
+        ga.T_batch = p->T_batch;
+        ga.t_solve_in = p->t_solve;
+        ga.grad_hist = p->grad_histories;
+        ga.grad_stride = p->grad_stride;
+        ga.grad_cost = p->grad_cost;
+        const size_t smem = L.smem_common() + (global ? 0 : L.smem_planes());
+        cudaError_t e;
+        if (global) {
+            e = cudaFuncSetAttribute(nastar::astar_generic_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e == cudaSuccess) nastar::astar_generic_kernel<true, false, true><<<grid, 32, smem, stream>>>(ga);
+        } else {
+            e = cudaFuncSetAttribute(nastar::astar_generic_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e == cudaSuccess) nastar::astar_generic_kernel<false, false, true><<<grid, 32, smem, stream>>>(ga);
+        }
+        if (e != cudaSuccess) return cuda_fail(e);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e);
+        return NASTAR_OK;
+    }
     nastar::W32Args a{};
     a.f.cost = p->cost;   a.f.cost_stride = p->cost_stride;
     a.f.start = p->start; a.f.start_stride = p->start_stride;

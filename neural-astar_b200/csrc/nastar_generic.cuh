@@ -1,4 +1,4 @@
-// nastar_fwd_generic.cuh — forward engine for maps of any shape (H or W > 32).
+// nastar_generic.cuh — engine for maps of any shape (H or W > 32): forward search and backward replay.
 //
 // Same state machine as the warp32 engine (DifferentiableAstar.forward loop + backtrack,
 // /root/reference/src/neural_astar/planner/differentiable_astar.py:187-255), one map per warp,
@@ -30,11 +30,37 @@ struct GenericLayout {
     __host__ __device__ size_t smem_planes() const { return size_t(npad()) * 13; }
     // per-CTA workspace slot of the kGlobal variant: g, f (fp32) + parent (u8)
     __host__ __device__ size_t slot_bytes() const { return (size_t(npad()) * 9 + 255) & ~size_t(255); }
+    // backward adds two fp32 planes (v, acc) per slot, always in the workspace
+    __host__ __device__ size_t bwd_bytes() const { return (size_t(npad()) * 8 + 255) & ~size_t(255); }
+    __host__ __device__ size_t slot_total(bool global_state, bool bwd) const {
+        return (global_state ? slot_bytes() : 0) + (bwd ? bwd_bytes() : 0);
+    }
 };
 
-template <bool kGlobal, bool kTrace>
-__global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_params p) {
+// forward parameters + the extra fields of nastar_bwd_params (same idea as W32Args)
+struct GenArgs {
+    nastar_fwd_params f;
+    float sqrt_w;
+    const int32_t* T_batch;
+    const int32_t* t_solve_in;
+    const float* grad_hist;
+    int64_t grad_stride;
+    float* grad_cost;
+};
+
+__device__ __forceinline__ float gen_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// kBwd = true replays the search for *T_batch steps and accumulates the closed-form gradient
+//  with a dense softmax pass per step over two fp32 planes (v, acc) kept in the
+// per-CTA workspace slot (L2 resident).  Functional, not yet tuned: O(N/32) per step.
+template <bool kGlobal, bool kTrace, bool kBwd>
+__global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const nastar_fwd_params& p = a.f;
     const int lane = threadIdx.x;
     const GenericLayout L(p.H, p.W);
     const int H = L.H, W = L.W, N = L.N, Wd = L.Wd;
@@ -52,10 +78,18 @@ __global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_
         F = reinterpret_cast<float*>(sp); sp += size_t(np) * 4;
         Par = reinterpret_cast<uint8_t*>(sp); sp += size_t(np);
     } else {
-        unsigned char* slot = static_cast<unsigned char*>(p.workspace) + size_t(blockIdx.x) * L.slot_bytes();
+        unsigned char* slot = static_cast<unsigned char*>(p.workspace) + size_t(blockIdx.x) * L.slot_total(true, kBwd);
         G = reinterpret_cast<float*>(slot);
         F = G + np;
         Par = reinterpret_cast<uint8_t*>(F + np);
+    }
+    float* V = nullptr;    // backward: v = exp(-f/sqrt(W)) of open cells, else 0
+    float* ACC = nullptr;  // backward: sum_t y_t[p] * (Gh[p] - <Gh, y_t>)
+    if (kBwd) {
+        unsigned char* slot = static_cast<unsigned char*>(p.workspace) + size_t(blockIdx.x) * L.slot_total(kGlobal, true) +
+                              (kGlobal ? L.slot_bytes() : 0);
+        V = reinterpret_cast<float*>(slot);
+        ACC = V + np;
     }
     uint32_t* sPass = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
     uint32_t* sOpen = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
@@ -66,7 +100,9 @@ __global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_
     uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
 
     const float gr = p.g_ratio, omg = p.one_minus_g_ratio;
-    const int T = p.T;
+    const int Tb = kBwd ? *a.T_batch : 0;
+    const int T = kBwd ? Tb : p.T;
+    const bool stationary_ok = (gr >= 0.5f);
     uint32_t bar_parity = 0;
     if (!kGlobal) {
         if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -120,12 +156,23 @@ __global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_
         const int gy = goal_idx / W, gx = goal_idx - gy * W;
         auto cost_at = [&](int i) -> float { return kGlobal ? __ldg(gCost + i) : sCost[i]; };
 
+        int ts_in = NASTAR_TS_CAPPED;
+        bool blocked = false;
+        const float* gG = nullptr;
+        if (kBwd) {
+            ts_in = a.t_solve_in[b];
+            blocked = (ts_in >= 0) && (ts_in < Tb - 1);   // goal clamp, differentiable_astar.py:222-223
+            gG = a.grad_hist + int64_t(b) * a.grad_stride;
+            for (int i = lane; i < N; i += 32) { V[i] = 0.f; ACC[i] = 0.f; }
+            __syncwarp();
+        }
         if (start_idx >= 0 && lane == 0) {
             const int sy = start_idx / W, sx = start_idx - sy * W;
             const float h0 = __fadd_rn(heuristic(sy, sx, gy, gx), cost_at(start_idx));
             const float f0 = f_value(gr, omg, 0.f, h0);
             G[start_idx] = 0.f;
             F[start_idx] = f0;
+            if (kBwd) V[start_idx] = expf(__fdiv_rn(-f0, a.sqrt_w));
             sOpen[sy * Wd + (sx >> 5)] = 1u << (sx & 31);
             sRmKey[sy] = fkey(f0);
             sRmCol[sy] = sx;
@@ -145,6 +192,28 @@ __global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_
         for (int t = 0; t < T; ++t) {
             const uint32_t m = __reduce_min_sync(kFull, bk);
             if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
+            if (kBwd) {
+                float s_ = 0.f, d_ = 0.f;
+                for (int i = lane; i < N; i += 32) {
+                    const float v = V[i];
+                    const float g = (blocked && i == goal_idx) ? 0.f : __ldg(gG + i);
+                    s_ += v;
+                    d_ = fmaf(g, v, d_);
+                }
+                s_ = gen_warp_sum(s_);
+                d_ = gen_warp_sum(d_);
+                const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
+                const float inv = (last ? float(Tb - t) : 1.f) / s_;
+                const float dd = d_ / s_;
+                for (int i = lane; i < N; i += 32) {
+                    const float v = V[i];
+                    if (v != 0.f) {
+                        const float g = (blocked && i == goal_idx) ? 0.f : __ldg(gG + i);
+                        ACC[i] = fmaf(v * inv, g - dd, ACC[i]);
+                    }
+                }
+                if (last) break;
+            }
             const int r = int(__reduce_min_sync(kFull, (bk == m) ? uint32_t(by) : 0x7FFFFFFFu));
             const int c = sRmCol[r];
             const int ind = r * W + c;
@@ -153,7 +222,10 @@ __global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_
             const bool solved = (ind == goal_idx);
             if (lane == 0) {
                 sClosed[r * Wd + (c >> 5)] |= 1u << (c & 31);
-                if (!solved) sOpen[r * Wd + (c >> 5)] &= ~(1u << (c & 31));
+                if (!solved) {
+                    sOpen[r * Wd + (c >> 5)] &= ~(1u << (c & 31));
+                    if (kBwd) V[ind] = 0.f;
+                }
             }
             __syncwarp();
             // rescan of row r over its remaining, pre-expansion open cells (ascending x => first min)
@@ -193,8 +265,9 @@ __global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_
                 Par[n] = uint8_t(k9);
                 atomicOr(&sOpen[y * Wd + (x >> 5)], 1u << (x & 31));
                 key = fkey(fn);
+                if (kBwd) V[n] = expf(__fdiv_rn(-fn, a.sqrt_w));
             }
-            if (solved) { t_solve = t; break; }
+            if (!kBwd && solved) { t_solve = t; break; }
             // per-row minimum of the freshly written keys: lanes {0,1,2} {3,4,5} {6,7,8}
             const uint32_t k1 = __shfl_down_sync(kFull, key, 1), k2 = __shfl_down_sync(kFull, key, 2);
             const int x1 = __shfl_down_sync(kFull, x, 1), x2 = __shfl_down_sync(kFull, x, 2);
@@ -227,6 +300,13 @@ __global__ void __launch_bounds__(32) astar_fwd_generic_kernel(const nastar_fwd_
         }
         __syncwarp();
 
+        if (kBwd) {
+            const float coef = -omg / a.sqrt_w;
+            float* gOut = a.grad_cost + int64_t(b) * N;
+            for (int i = lane; i < N; i += 32) gOut[i] = coef * ACC[i];
+            __syncwarp();
+            continue;
+        }
         // ---- backtrack (differentiable_astar.py:96-125): follow direction codes ---------------
         if (lane == 0) {
             sPath[gy * Wd + (gx >> 5)] |= 1u << (gx & 31);

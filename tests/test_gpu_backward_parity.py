@@ -129,3 +129,28 @@ def test_module_api_backward_reaches_encoder(native, oracle):
     Tb = min(256, int(max(1 + ref.t_solve.max(), 256 if (ref.t_solve < 0).any() else 0)))
     want = oracle.backward(c_np, g.start[:32], g.goal[:32], g.obst[:32], Gmat, Tb)
     assert _relerr(cost.grad.cpu().numpy(), want) < TOL
+
+
+@pytest.mark.parametrize("H,W,B", [(64, 64, 6), (40, 48, 5), (33, 70, 4), (144, 136, 2)])
+def test_generic_engine_backward_vs_oracle(native, oracle, H, W, B):
+    """Backward for maps larger than 32x32 (engine 2: smem state; engine 3: HBM workspace)."""
+    rng = np.random.RandomState(H * 7 + W)
+    obst = (rng.rand(B, 1, H, W) > 0.15).astype(np.float32)
+    start = np.zeros((B, 1, H, W), np.float32)
+    goal = np.zeros((B, 1, H, W), np.float32)
+    obst[:, 0, 0, 0] = obst[:, 0, -1, -1] = 1
+    start[:, 0, 0, 0] = 1
+    goal[:, 0, -1, -1] = 1
+    ref = oracle.forward(obst, start, goal, obst, mode="spec")
+    keep = ref.t_solve >= 0
+    assert keep.sum() >= 1
+    obst, start, goal = obst[keep], start[keep], goal[keep]
+    B = obst.shape[0]
+    cost = (1.0 / (1.0 + np.exp(-rng.randn(B, 1, H, W)))).astype(np.float32)
+    G = rng.randn(B, 1, H, W).astype(np.float32)
+    for Tmax, training in ((1.0, False), (0.1, True)):
+        T = int((Tmax if training else 1.0) * W * W)
+        _, gc, Tb, ts = _fwd_bwd(native, cost, start, goal, obst, G, 0.5, T)
+        want = oracle.backward(cost, start, goal, obst, G, Tb, g_ratio=0.5)
+        assert np.isfinite(gc).all()
+        assert _relerr(gc, want) < TOL, (H, W, Tmax)
