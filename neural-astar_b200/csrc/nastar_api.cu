@@ -25,6 +25,25 @@ int num_sms() {
     return n;
 }
 
+// one-time fill of the 32x32 heuristic table on the current device (stream-ordered before first use)
+cudaError_t ensure_heur32(cudaStream_t stream) {
+    static std::atomic<uint64_t> done_mask{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = uint64_t(1) << (dev & 63);
+    if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    nastar::heur32_init_kernel<<<4, 256, 0, stream>>>();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // later launches on OTHER streams must also see the table: finish the fill before publishing
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    done_mask.fetch_or(bit, std::memory_order_release);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaSuccess;
+}
+
 int generic_slots(int B) {
     const int cap = num_sms() * kGlobalCtasPerSm;
     return B < cap ? B : cap;
@@ -95,6 +114,8 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         if (e != cudaSuccess) return cuda_fail(e);
     }
     if (engine == 1) {
+        cudaError_t he = ensure_heur32(stream);
+        if (he != cudaSuccess) return cuda_fail(he);
         nastar::W32Args a{};
         a.f = *p;
         if (p->trace)
@@ -173,6 +194,10 @@ int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e);
         return NASTAR_OK;
+    }
+    {
+        cudaError_t he = ensure_heur32(stream);
+        if (he != cudaSuccess) return cuda_fail(he);
     }
     nastar::W32Args a{};
     a.f.cost = p->cost;   a.f.cost_stride = p->cost_stride;

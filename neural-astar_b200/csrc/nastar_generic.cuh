@@ -130,20 +130,70 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             (void)tma_ok;
         }
         int start_idx = -1, goal_idx = -1;
-        for (int y = 0; y < H; ++y) {
-            for (int w = 0; w < Wd; ++w) {
-                const int x = (w << 5) + lane;
-                const bool in = x < W;
-                const int i = y * W + x;
-                const float vo = in ? __ldg(gObst + i) : 0.f;
-                const float vs = in ? __ldg(gStart + i) : 0.f;
-                const float vg = in ? __ldg(gGoal + i) : 0.f;
-                const uint32_t wo = __ballot_sync(kFull, vo != 0.f);
-                const uint32_t ws = __ballot_sync(kFull, vs != 0.f);
-                const uint32_t wg = __ballot_sync(kFull, vg != 0.f);
-                if (lane == 0) sPass[y * Wd + w] = wo;
-                if (start_idx < 0 && ws) start_idx = y * W + (w << 5) + __ffs(ws) - 1;
-                if (goal_idx < 0 && wg) goal_idx = y * W + (w << 5) + __ffs(wg) - 1;
+        const bool vec = ((W & 31) == 0) && aligned16(gObst) && aligned16(gStart) && aligned16(gGoal);
+        if (vec) {
+            // Rows are whole 32-bit words (flat bit index == row-word index): stream the planes with
+            // 128-bit loads, kUnroll segments of 128 cells in flight per plane (the prologue is a pure
+            // HBM stream; with one warp per map the only way to cover DRAM latency is load-level parallelism)
+            constexpr int kUnroll = 8;
+            const int nseg = N >> 7;
+            const float4* o4 = reinterpret_cast<const float4*>(gObst);
+            const float4* s4 = reinterpret_cast<const float4*>(gStart);
+            const float4* g4 = reinterpret_cast<const float4*>(gGoal);
+            for (int seg0 = 0; seg0 < nseg; seg0 += kUnroll) {
+                float4 vo[kUnroll], vs[kUnroll], vg[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int q = ((seg0 + u) << 5) + lane;
+                    const bool in = (seg0 + u) < nseg;
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    vo[u] = in ? __ldg(o4 + q) : z;
+                    vs[u] = in ? __ldg(s4 + q) : z;
+                    vg[u] = in ? __ldg(g4 + q) : z;
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    if ((seg0 + u) < nseg) {
+                        // lane l holds cells 4l..4l+3 of the segment; word k = lanes 8k..8k+7
+                        uint32_t nib = (vo[u].x != 0.f ? 1u : 0u) | (vo[u].y != 0.f ? 2u : 0u) |
+                                       (vo[u].z != 0.f ? 4u : 0u) | (vo[u].w != 0.f ? 8u : 0u);
+                        uint32_t word = nib << ((lane & 7) << 2);
+                        word |= __shfl_xor_sync(kFull, word, 1);
+                        word |= __shfl_xor_sync(kFull, word, 2);
+                        word |= __shfl_xor_sync(kFull, word, 4);
+                        if ((lane & 7) == 0) sPass[((seg0 + u) << 2) + (lane >> 3)] = word;
+                        const bool hs = (vs[u].x != 0.f) | (vs[u].y != 0.f) | (vs[u].z != 0.f) | (vs[u].w != 0.f);
+                        const bool hg = (vg[u].x != 0.f) | (vg[u].y != 0.f) | (vg[u].z != 0.f) | (vg[u].w != 0.f);
+                        const uint32_t bs = __ballot_sync(kFull, hs), bg = __ballot_sync(kFull, hg);
+                        if (start_idx < 0 && bs) {
+                            const int src = __ffs(bs) - 1;
+                            const int e = (vs[u].x != 0.f) ? 0 : (vs[u].y != 0.f) ? 1 : (vs[u].z != 0.f) ? 2 : 3;
+                            start_idx = ((seg0 + u) << 7) + (src << 2) + __shfl_sync(kFull, e, src);
+                        }
+                        if (goal_idx < 0 && bg) {
+                            const int src = __ffs(bg) - 1;
+                            const int e = (vg[u].x != 0.f) ? 0 : (vg[u].y != 0.f) ? 1 : (vg[u].z != 0.f) ? 2 : 3;
+                            goal_idx = ((seg0 + u) << 7) + (src << 2) + __shfl_sync(kFull, e, src);
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int y = 0; y < H; ++y) {
+                for (int w = 0; w < Wd; ++w) {
+                    const int x = (w << 5) + lane;
+                    const bool in = x < W;
+                    const int i = y * W + x;
+                    const float vo = in ? __ldg(gObst + i) : 0.f;
+                    const float vs = in ? __ldg(gStart + i) : 0.f;
+                    const float vg = in ? __ldg(gGoal + i) : 0.f;
+                    const uint32_t wo = __ballot_sync(kFull, vo != 0.f);
+                    const uint32_t ws = __ballot_sync(kFull, vs != 0.f);
+                    const uint32_t wg = __ballot_sync(kFull, vg != 0.f);
+                    if (lane == 0) sPass[y * Wd + w] = wo;
+                    if (start_idx < 0 && ws) start_idx = y * W + (w << 5) + __ffs(ws) - 1;
+                    if (goal_idx < 0 && wg) goal_idx = y * W + (w << 5) + __ffs(wg) - 1;
+                }
             }
         }
         if (goal_idx < 0) goal_idx = 0;
@@ -329,11 +379,27 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         // ---- epilogue: coalesced stores --------------------------------------------------------
         float* gHist = p.histories + int64_t(b) * N;
         long long* gPath = reinterpret_cast<long long*>(p.paths) + int64_t(b) * N;
-        for (int y = 0; y < H; ++y) {
-            for (int x = lane; x < W; x += 32) {
-                const int wi = y * Wd + (x >> 5);
-                gHist[y * W + x] = ((sClosed[wi] >> (x & 31)) & 1u) ? 1.f : 0.f;
-                gPath[y * W + x] = ((sPath[wi] >> (x & 31)) & 1u) ? 1ll : 0ll;
+        if (((W & 31) == 0) && aligned16(gHist) && aligned16(gPath)) {
+            // flat bit index == row-word index: each lane expands 4 cells per segment into one 128-bit
+            // histories store and two 128-bit paths stores (fully coalesced)
+            const int nseg = N >> 7;
+            const int sh = (lane & 7) << 2;
+            for (int seg = 0; seg < nseg; ++seg) {
+                const int wi = (seg << 2) + (lane >> 3);
+                const uint32_t cb = sClosed[wi] >> sh, pb = sPath[wi] >> sh;
+                const int q = (seg << 5) + lane;
+                reinterpret_cast<float4*>(gHist)[q] = make_float4((cb & 1u) ? 1.f : 0.f, (cb & 2u) ? 1.f : 0.f,
+                                                                  (cb & 4u) ? 1.f : 0.f, (cb & 8u) ? 1.f : 0.f);
+                reinterpret_cast<longlong2*>(gPath)[2 * q] = make_longlong2((pb & 1u) ? 1ll : 0ll, (pb & 2u) ? 1ll : 0ll);
+                reinterpret_cast<longlong2*>(gPath)[2 * q + 1] = make_longlong2((pb & 4u) ? 1ll : 0ll, (pb & 8u) ? 1ll : 0ll);
+            }
+        } else {
+            for (int y = 0; y < H; ++y) {
+                for (int x = lane; x < W; x += 32) {
+                    const int wi = y * Wd + (x >> 5);
+                    gHist[y * W + x] = ((sClosed[wi] >> (x & 31)) & 1u) ? 1.f : 0.f;
+                    gPath[y * W + x] = ((sPath[wi] >> (x & 31)) & 1u) ? 1ll : 0ll;
+                }
             }
         }
         if (lane == 0) {

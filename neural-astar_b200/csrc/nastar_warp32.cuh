@@ -38,6 +38,16 @@ struct W32Args {
 
 constexpr int kCells = 1024;  // padded 32 x 32
 
+// heuristic(|dy|, |dx|) for every offset on a 32x32 grid, filled once per device by
+// heur32_init_kernel with the very same device function the generic engine evaluates inline —
+// the per-map h pass becomes one cached load + one add per cell instead of an IEEE sqrt chain.
+__device__ float g_heur32[kCells];
+
+__global__ void heur32_init_kernel() {
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i < kCells) g_heur32[i] = heuristic(i >> 5, i & 31, 0, 0);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -46,7 +56,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 struct __align__(16) W32Smem {
     float cost[kCells];        // staged cost plane (padded)
-    float f[kCells];           // f = g_ratio*g + (1-g_ratio)*h of opened cells
+    uint32_t key[kCells];      // order-preserving key of f = g_ratio*g + (1-g_ratio)*h, opened cells only
     float2 ghbuf[kCells + 4];  // {g, h} per cell at ghbuf[2 + rc]; 2 guard cells on either side make the
                                // c-1 / c+1 window loads of the first/last cell addressable (16-B aligned body)
     uint16_t par[kCells];      // parent cell id (padded rc) of opened cells
@@ -79,7 +89,7 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
     if (tma) {
         // flat layout == padded layout: bulk-copy whole planes (start/goal/obstacles are parked in the
         // f and {g,h} planes, which are not live yet)
-        float* tStart = S.f;
+        float* tStart = reinterpret_cast<float*>(S.key);
         float* tGoal = reinterpret_cast<float*>(sGH);
         float* tObst = tGoal + kCells;
         uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
@@ -107,31 +117,48 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
             if (goal_rc < 0 && wg) goal_rc = (y << 5) + __ffs(wg) - 1;
         }
     } else {
+        // W < 32 (or unaligned planes): rows are shorter than a warp; issue 8 rows of loads per plane
+        // before consuming them so that DRAM latency is paid H/8 times, not H times
         const bool in = lane < W;
-#pragma unroll 4
-        for (int y = 0; y < H; ++y) {
-            const int i = y * W + lane;
-            const float vc = in ? __ldg(gCost + i) : 0.f;
-            const float vo = obst_is_cost ? vc : (in ? __ldg(gObst + i) : 0.f);
-            const float vs = in ? __ldg(gStart + i) : 0.f;
-            const float vg = in ? __ldg(gGoal + i) : 0.f;
-            S.cost[(y << 5) + lane] = vc;
-            const uint32_t wo = __ballot_sync(kFull, vo != 0.f);
-            const uint32_t ws = __ballot_sync(kFull, vs != 0.f);
-            const uint32_t wg = __ballot_sync(kFull, vg != 0.f);
-            if (lane == y) pass = wo;
-            if (start_rc < 0 && ws) start_rc = (y << 5) + __ffs(ws) - 1;
-            if (goal_rc < 0 && wg) goal_rc = (y << 5) + __ffs(wg) - 1;
+        constexpr int kRows = 8;
+        for (int y0 = 0; y0 < H; y0 += kRows) {
+            float vc[kRows], vo[kRows], vs[kRows], vg[kRows];
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const bool ok = in && (y0 + u < H);
+                const int i = (y0 + u) * W + lane;
+                vc[u] = ok ? __ldg(gCost + i) : 0.f;
+                vo[u] = obst_is_cost ? vc[u] : (ok ? __ldg(gObst + i) : 0.f);
+                vs[u] = ok ? __ldg(gStart + i) : 0.f;
+                vg[u] = ok ? __ldg(gGoal + i) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < kRows; ++u) {
+                const int y = y0 + u;
+                if (y < H) {
+                    S.cost[(y << 5) + lane] = vc[u];
+                    const uint32_t wo = __ballot_sync(kFull, vo[u] != 0.f);
+                    const uint32_t ws = __ballot_sync(kFull, vs[u] != 0.f);
+                    const uint32_t wg = __ballot_sync(kFull, vg[u] != 0.f);
+                    if (lane == y) pass = wo;
+                    if (start_rc < 0 && ws) start_rc = (y << 5) + __ffs(ws) - 1;
+                    if (goal_rc < 0 && wg) goal_rc = (y << 5) + __ffs(wg) - 1;
+                }
+            }
         }
     }
     if (goal_rc < 0) goal_rc = 0;  // argmax of an all-zero plane (differentiable_astar.py:197)
     const int gy = goal_rc >> 5, gx = goal_rc & 31;
     __syncwarp();
     // h = heuristic + cost (:191-192), one row per iteration; overwrites the parked planes
-#pragma unroll 4
-    for (int y = 0; y < H; ++y) {
-        const int i = (y << 5) + lane;
-        sGH[i] = make_float2(0.f, __fadd_rn(heuristic(y, lane, gy, gx), S.cost[i]));
+    {
+        const int adx = (lane > gx) ? (lane - gx) : (gx - lane);
+#pragma unroll 8
+        for (int y = 0; y < H; ++y) {
+            const int i = (y << 5) + lane;
+            const int ady = (y > gy) ? (y - gy) : (gy - y);
+            sGH[i] = make_float2(0.f, __fadd_rn(__ldg(&g_heur32[(ady << 5) | adx]), S.cost[i]));
+        }
     }
     __syncwarp();
 
@@ -179,7 +206,7 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         const float f0 = f_value(gr, omg, 0.f, sGH[start_rc].y);
         if (lane == 0) {
             S.par[start_rc] = uint16_t(goal_rc);
-            S.f[start_rc] = f0;                      // g = 0 already (:193)
+            S.key[start_rc] = fkey(f0);              // g = 0 already (:193)
             if (kBwd) sV[start_rc] = expf(__fdiv_rn(-f0, a.sqrt_w));  // :207
         }
         if (lane == (start_rc >> 5)) {
@@ -197,10 +224,10 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
     // nothing changes): the backward then adds them in one go
     const bool stationary_ok = (gr >= 0.5f);
     int t_solve = NASTAR_TS_CAPPED;
-    int steps = 0;
     int32_t* trace = kTrace ? (p.trace + int64_t(b) * p.T) : nullptr;
     const float2* ghrow = sGH + (lane << 5);      // this lane's row of {g,h}
-    for (int t = 0; t < T; ++t) {
+    int t = 0;
+    for (; t < T; ++t) {
         // -- select: lexicographic arg-min of (f key, row, col) with two REDUX.MINs -----------
         const uint32_t m = __reduce_min_sync(kFull, rm_key);
         if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
@@ -236,7 +263,6 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         }
         const uint32_t ind = __reduce_min_sync(kFull, (rm_key == m) ? uint32_t((lane << 5) | rm_col) : 0xFFFFFFFFu);
         const int r = int(ind >> 5), c = int(ind & 31u);
-        steps = t + 1;
         if (kTrace && lane == 0) trace[t] = r * W + c;
         const bool solved = (int(ind) == goal_rc);          // :219-220
         const uint32_t m1 = 1u << c;                        // column masks of the 3-wide window;
@@ -244,8 +270,8 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         // -- rescan inputs for row r (pre-expansion open cells minus the selected one); stale f
         //    values of cells relaxed this step are upper bounds and the fresh keys are merged below
         const uint32_t open_r = (kBwd && solved) ? S.open_row[r] : (S.open_row[r] & ~m1);
-        const float frs = S.f[(r << 5) + lane];
-        const uint32_t rs_key = ((open_r >> lane) & 1u) ? fkey(frs) : kKeyInf;
+        const uint32_t krs = S.key[(r << 5) + lane];
+        const uint32_t rs_key = ((open_r >> lane) & 1u) ? krs : kKeyInf;
         // -- expansion inputs ----------------------------------------------------------------
         const int dr = lane - r;
         const bool isr = (dr == 0);
@@ -274,16 +300,17 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         const float f2n = __fadd_rn(ag, __fmul_rn(omg, n2.y));
         const bool u0 = (upd & m0) != 0u, u1 = (upd & m1) != 0u, u2 = (upd & m2) != 0u;
         const int cell = (lane << 5) + c;
-        if (u0) { sGH[cell - 1].x = g2; S.f[cell - 1] = f0n; S.par[cell - 1] = uint16_t(ind); }   // :238, :246-249
-        if (u1) { sGH[cell].x = g2;     S.f[cell] = f1n;     S.par[cell] = uint16_t(ind); }
-        if (u2) { sGH[cell + 1].x = g2; S.f[cell + 1] = f2n; S.par[cell + 1] = uint16_t(ind); }
+        const uint32_t q0 = fkey(f0n), q1 = fkey(f1n), q2 = fkey(f2n);
+        if (u0) { sGH[cell - 1].x = g2; S.key[cell - 1] = q0; S.par[cell - 1] = uint16_t(ind); }   // :238, :246-249
+        if (u1) { sGH[cell].x = g2;     S.key[cell] = q1;     S.par[cell] = uint16_t(ind); }
+        if (u2) { sGH[cell + 1].x = g2; S.key[cell + 1] = q2; S.par[cell + 1] = uint16_t(ind); }
         if (kBwd) {
             if (u0) sV[cell - 1] = expf(__fdiv_rn(-f0n, a.sqrt_w));   // :207
             if (u1) sV[cell] = expf(__fdiv_rn(-f1n, a.sqrt_w));
             if (u2) sV[cell + 1] = expf(__fdiv_rn(-f2n, a.sqrt_w));
         }
         // fold the fresh keys (ascending column, strict < keeps the lowest column on ties)
-        const uint32_t k0 = u0 ? fkey(f0n) : kKeyInf, k1 = u1 ? fkey(f1n) : kKeyInf, k2 = u2 ? fkey(f2n) : kKeyInf;
+        const uint32_t k0 = u0 ? q0 : kKeyInf, k1 = u1 ? q1 : kKeyInf, k2 = u2 ? q2 : kKeyInf;
         uint32_t bk = k0;
         int bc = c - 1;
         if (k1 < bk) { bk = k1; bc = c; }
@@ -300,6 +327,8 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         __syncwarp();
     }
     __syncwarp();
+    // selection steps executed: t on exhaustion / cap, t+1 when the loop left through the solve step
+    const int steps = (t_solve >= 0) ? (t + 1) : t;
 
     if (kBwd) {
         // dL/dcost = -(1-g_ratio)/sqrt(W) * acc   (h = heuristic + cost, f = g_ratio*g + (1-g_ratio)*h)

@@ -1,0 +1,90 @@
+"""Config 3 (scripts/train.py semantics) end to end on the GPU vs the reference's CPU training curve.
+
+Golden: tests/golden/train_curve_mazes032.npz (tests/golden/make_golden_train.py ran the reference's
+NeuralAstar + autograd + RMSprop for 4 steps on CPU).  The search is discrete, so tiny differences
+between cuDNN and MKL-DNN convolutions can flip individual selections; the curve must agree to 2 %.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_curve_mazes032.npz")
+
+
+def _batch():
+    z = np.load(GOLD)
+    B, H, W = (int(v) for v in z["shape"])
+    N = H * W
+
+    def bits(k):
+        return np.unpackbits(z[k], axis=1)[:, :N].reshape(B, 1, H, W).astype(np.float32)
+
+    def onehot(k):
+        x = np.zeros((B, N), np.float32)
+        x[np.arange(B), z[k]] = 1
+        return x.reshape(B, 1, H, W)
+
+    return z, bits("obst_bits"), onehot("start_idx"), onehot("goal_idx"), bits("opt_bits")
+
+
+def test_training_curve_matches_reference():
+    from types import SimpleNamespace
+
+    from neural_astar.planner import NeuralAstar
+    from neural_astar.utils.training import PlannerModule
+
+    z, maps, starts, goals, opts = _batch()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # fp32 convolutions, like the CPU reference
+    try:
+        torch.manual_seed(1234)
+        planner = NeuralAstar(encoder_input="m+", encoder_arch="CNN", encoder_depth=4, Tmax=0.25)
+        init_abs = float(sum(p.detach().abs().sum() for p in planner.parameters()))
+        assert init_abs == pytest.approx(float(z["init_abs"]), rel=1e-6), "same seed must give the reference's init"
+        module = PlannerModule(planner, SimpleNamespace(params=SimpleNamespace(lr=1e-3))).cuda()
+        opt = module.configure_optimizers()
+        assert isinstance(opt, torch.optim.RMSprop)
+        batch = [torch.from_numpy(x).cuda() for x in (maps, starts, goals, opts)]
+        module.train()
+        losses, hist_sums = [], []
+        for step in range(len(z["losses"])):
+            opt.zero_grad()
+            loss = module.training_step(batch, step)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+            with torch.no_grad():
+                hist_sums.append(float(module(batch[0], batch[1], batch[2]).histories.sum()))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    ref = z["losses"]
+    assert losses[0] == pytest.approx(float(ref[0]), rel=2e-3), (losses, ref)   # same init -> same first loss
+    np.testing.assert_allclose(losses, ref, rtol=2e-2)
+    final_abs = float(sum(p.detach().abs().sum() for p in planner.parameters()))
+    assert final_abs == pytest.approx(float(z["final_abs"]), rel=1e-3)
+
+
+def test_validation_metrics_on_device():
+    """validation_step logs p_opt / p_exp / h_mean (utils/training.py:63-87) without leaving the GPU."""
+    from types import SimpleNamespace
+
+    from neural_astar.planner import VanillaAstar
+    from neural_astar.utils.training import PlannerModule, planner_metrics
+
+    z, maps, starts, goals, opts = _batch()
+    batch = [torch.from_numpy(x[:32]).cuda() for x in (maps, starts, goals, opts)]
+    module = PlannerModule(VanillaAstar(), SimpleNamespace(params=SimpleNamespace(lr=1e-3))).cuda().eval()
+    with torch.no_grad():
+        module.validation_step(batch, 0)
+    if hasattr(module, "logged"):
+        lg = module.logged
+        assert lg["metrics/p_opt"] == 1.0 and lg["metrics/p_exp"] == 0.0   # planner == vanilla baseline
+        assert lg["metrics/h_mean"] == pytest.approx(0.0, abs=1e-6)
+    va = VanillaAstar().cuda()(batch[0], batch[1], batch[2])
+    # vanilla A* finds optimal-length paths on every map (path length == optimal)
+    assert torch.equal(va.paths.sum((1, 2, 3)), (batch[3].sum((1, 2, 3)) + 1).long())
+    assert planner_metrics(va, va) == (1.0, 0.0, pytest.approx(0.0, abs=1e-6))
