@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         float2 n0 = make_float2(0.f, 0.f), n1 = n0, n2 = n0;
         if (near) { n0 = ghrow[c - 1]; n1 = ghrow[c]; n2 = ghrow[c + 1]; }   // guard cells make c-1/c+1 safe
         const float g2 = __fadd_rn(sGH[ind].x, S.cost[ind]);               // :234, cost of the SELECTED node
+        __syncwarp();   // every shared-memory read of this step precedes every write below (no intra-warp WAR)
         // -- closed/open update of the selected cell (:222-225) ------------------------------
         if (isr) {
             closed |= m1;

@@ -1,0 +1,20 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck): every engine, fwd + bwd."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "neural-astar_b200"), os.path.join(ROOT, "tests")]
+import numpy as np, torch
+from neural_astar import _native
+rng = np.random.RandomState(0)
+for (H, W, B) in ((32, 32, 6), (12, 12, 5), (7, 5, 3), (64, 64, 3), (40, 48, 2), (144, 136, 2)):
+    obst = (rng.rand(B, 1, H, W) > 0.2).astype(np.float32)
+    start = np.zeros_like(obst); goal = np.zeros_like(obst)
+    obst[:, 0, 0, 0] = obst[:, 0, -1, -1] = 1; start[:, 0, 0, 0] = 1; goal[:, 0, -1, -1] = 1
+    cost = (obst * (0.5 + rng.rand(B, 1, H, W))).astype(np.float32)
+    c, s, g, o = (torch.from_numpy(x).cuda() for x in (cost, start, goal, obst))
+    for T in (W * W, max(1, (W * W) // 8)):
+        hist, paths, ts, ns, tr = _native.forward(c, s, g, o, 0.5, T, True)
+        Tb = _native.batch_steps(ts, ns, T)
+        gc = _native.backward(c, s, g, o, torch.randn_like(c), Tb, ts, 0.5)
+    hist2 = _native.forward(o, s, g, o, 0.5, W * W)[0]   # aliasing path
+    torch.cuda.synchronize()
+    print(H, W, "ok", float(hist.sum()), float(gc.abs().sum()) > 0)
