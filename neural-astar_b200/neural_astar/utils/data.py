@@ -74,14 +74,42 @@ class MazeDataset(data.Dataset):
         return self.map_designs.shape[0]
 
     def __getitem__(self, index: int):
+        """Same samples and the same np.random consumption as the reference (:152-166), but the per-map work
+        that does not depend on the draw (percentile bands, the policy's successor table) is computed once
+        and cached — at GPU training speeds the reference's per-sample NumPy work is the bottleneck
+        (SURVEY.md 8(f) rank 4)."""
         map_design = self.map_designs[index][np.newaxis]
         goal_map = self.goal_maps[index]
-        starts, trajs = [], []
-        for _ in range(self.num_starts):
-            s = self.get_random_start_map(self.opt_dists[index])
-            starts.append(s)
-            trajs.append(self.get_opt_traj(s, goal_map, self.opt_policies[index]))
-        return map_design, np.concatenate(starts), goal_map, np.concatenate(trajs)
+        bands, succ = self._prepared(index)
+        H, W = goal_map.shape[-2:]
+        goal_flat = int(np.argmax(goal_map.reshape(-1)))
+        starts = np.zeros((self.num_starts, H, W), np.float32)
+        trajs = np.zeros((self.num_starts, H, W), np.float32)
+        for k in range(self.num_starts):
+            r = np.random.randint(0, len(bands))          # same draw order as get_random_start_map
+            loc = int(np.random.choice(bands[r]))
+            starts[k].reshape(-1)[loc] = 1.0
+            flat = trajs[k].reshape(-1)
+            while loc != goal_flat:
+                flat[loc] = 1.0
+                loc = int(succ[loc])
+                assert flat[loc] == 0.0, "Revisiting the same position while following the optimal policy"
+        return map_design, starts, goal_map, trajs
+
+    def _prepared(self, index: int):
+        cache = self.__dict__.setdefault("_cache", {})
+        hit = cache.get(index)
+        if hit is None:
+            od = self.opt_dists[index].flatten()
+            th = np.percentile(od[od > od.min()], 100.0 * (1 - self.pcts))
+            bands = [np.where((od >= th[r + 1]) & (od <= th[r]))[0] for r in range(len(th) - 1)]
+            policy = self.opt_policies[index]                       # [A, 1, H, W] one-hot over actions
+            H, W = policy.shape[-2:]
+            act = policy.reshape(policy.shape[0], -1).argmax(0)      # first maximal action, like np.argmax
+            moves = np.array([m[1] * W + m[2] for m in _ACTION_TO_MOVE])
+            succ = np.arange(H * W) + moves[act]
+            hit = cache[index] = (bands, succ)
+        return hit
 
     def get_random_start_map(self, opt_dist: np.ndarray) -> np.ndarray:
         """Pick a start uniformly inside one of the 55-70 / 70-85 / 85-100 percentile bands of the optimal

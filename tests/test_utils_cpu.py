@@ -124,3 +124,20 @@ def test_training_helpers(tmp_path):
     msg = NeuralAstar(encoder_depth=1).load_state_dict({k: v for k, v in sd.items() if not k.startswith("vanilla")},
                                                         strict=False)
     assert not msg.missing_keys
+
+
+def test_cached_getitem_equals_reference_style_methods(npz):
+    """The cached fast path of __getitem__ draws the same samples (and consumes np.random identically) as the
+    reference-style public methods get_random_start_map / get_opt_traj."""
+    from neural_astar.utils.data import MazeDataset
+
+    ds = MazeDataset(npz, "train")
+    for i in range(len(ds)):
+        np.random.seed(100 + i)
+        s_ref = ds.get_random_start_map(ds.opt_dists[i])
+        t_ref = ds.get_opt_traj(s_ref, ds.goal_maps[i], ds.opt_policies[i])
+        after_ref = np.random.rand()
+        np.random.seed(100 + i)
+        _, s, _, t = ds[i]
+        after = np.random.rand()
+        assert np.array_equal(s, s_ref) and np.array_equal(t, t_ref) and after == after_ref
