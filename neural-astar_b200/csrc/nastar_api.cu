@@ -13,7 +13,7 @@ std::atomic<uint64_t> g_launches{0};
 cudaError_t g_last_err = cudaSuccess;
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
-constexpr int kGlobalCtasPerSm = 6;
+constexpr int kGlobalCtasPerSm = 8;
 
 int num_sms() {
     static int n = 0;

@@ -24,8 +24,9 @@ struct GenericLayout {
     int H, W, N, Wd, nbits;  // nbits = H*Wd words per bit array
     __host__ __device__ GenericLayout(int h, int w) : H(h), W(w), N(h * w), Wd((w + 31) >> 5), nbits(h * ((w + 31) >> 5)) {}
     __host__ __device__ int npad() const { return (N + 3) & ~3; }
-    // shared-memory bytes that every variant needs: 4 bit arrays + row-min cache + mbarrier
-    __host__ __device__ size_t smem_common() const { return size_t(4) * nbits * 4 + size_t(H) * 8 + 16; }
+    // shared-memory bytes that every variant needs: 3 bit arrays (the path rows reuse the passable rows once the
+    // search is over) + row-min cache + mbarrier
+    __host__ __device__ size_t smem_common() const { return size_t(3) * nbits * 4 + size_t(H) * 8 + 16; }
     // planes kept in shared memory by the !kGlobal variant: cost, g, f (fp32) + parent (u8)
     __host__ __device__ size_t smem_planes() const { return size_t(npad()) * 13; }
     // per-CTA workspace slot of the kGlobal variant: g, f (fp32) + parent (u8)
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
     uint32_t* sPass = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
     uint32_t* sOpen = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
     uint32_t* sClosed = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
-    uint32_t* sPath = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
+    uint32_t* sPath = sPass;  // the passable rows are dead once the loop ends; the backtrack reuses them
     uint32_t* sRmKey = reinterpret_cast<uint32_t*>(sp); sp += size_t(H) * 4;
     int32_t* sRmCol = reinterpret_cast<int32_t*>(sp); sp += size_t(H) * 4;
     uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             }
         }
         if (goal_idx < 0) goal_idx = 0;
-        for (int i = lane; i < L.nbits; i += 32) { sOpen[i] = 0u; sClosed[i] = 0u; sPath[i] = 0u; }
+        for (int i = lane; i < L.nbits; i += 32) { sOpen[i] = 0u; sClosed[i] = 0u; }
         for (int y = lane; y < H; y += 32) { sRmKey[y] = kKeyInf; sRmCol[y] = 0; }
         if (!kGlobal) {
             if (((N & 3) == 0) && aligned16(gCost)) { mbar_wait(bar, bar_parity); bar_parity ^= 1u; }
@@ -355,9 +356,11 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             float* gOut = a.grad_cost + int64_t(b) * N;
             for (int i = lane; i < N; i += 32) gOut[i] = coef * ACC[i];
             __syncwarp();
-            continue;
         }
+        if (!kBwd) {
         // ---- backtrack (differentiable_astar.py:96-125): follow direction codes ---------------
+        for (int i = lane; i < L.nbits; i += 32) sPath[i] = 0u;   // sPath aliases sPass
+        __syncwarp();
         if (lane == 0) {
             sPath[gy * Wd + (gx >> 5)] |= 1u << (gx & 31);
             const bool goal_has_parent = (sOpen[gy * Wd + (gx >> 5)] >> (gx & 31)) & 1u;
@@ -406,6 +409,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             if (p.t_solve) p.t_solve[b] = t_solve;
             if (p.n_steps) p.n_steps[b] = steps;
         }
+        }  // !kBwd
         __syncwarp();
     }
 }
