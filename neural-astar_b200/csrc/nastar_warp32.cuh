@@ -59,7 +59,7 @@ struct __align__(16) W32Smem {
     uint32_t key[kCells];      // order-preserving key of f = g_ratio*g + (1-g_ratio)*h, opened cells only
     float2 ghbuf[kCells + 4];  // {g, h} per cell at ghbuf[2 + rc]; 2 guard cells on either side make the
                                // c-1 / c+1 window loads of the first/last cell addressable (16-B aligned body)
-    uint16_t par[kCells];      // parent cell id (padded rc) of opened cells
+    int8_t par[kCells];        // parent link of opened cells as a signed offset: parent = rc - par[rc], in [-33, 33]
     uint32_t open_row[32];     // every lane's open row, refreshed each step (rescan input)
     uint32_t bits_a[32];       // closed rows for the epilogue
     uint32_t bits_b[32];       // path rows for the epilogue
@@ -67,7 +67,7 @@ struct __align__(16) W32Smem {
 };
 
 template <bool kTrace, bool kBwd>
-__global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
+__global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     __shared__ W32Smem S;
     extern __shared__ __align__(16) float sV[];  // backward only: v = exp(-f/sqrt(W)) of open cells, else 0
     const nastar_fwd_params& p = a.f;
@@ -201,11 +201,10 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         }
         __syncwarp();
     }
-    if (lane == 0) S.par[goal_rc] = uint16_t(goal_rc);  // parents initialised to the goal (:195-198)
+    if (lane == 0) S.par[goal_rc] = 0;  // parents are initialised to the goal (:195-198): a self link at the goal
     if (start_rc >= 0) {
         const float f0 = f_value(gr, omg, 0.f, sGH[start_rc].y);
         if (lane == 0) {
-            S.par[start_rc] = uint16_t(goal_rc);
             S.key[start_rc] = fkey(f0);              // g = 0 already (:193)
             if (kBwd) sV[start_rc] = expf(__fdiv_rn(-f0, a.sqrt_w));  // :207
         }
@@ -302,9 +301,10 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
         const bool u0 = (upd & m0) != 0u, u1 = (upd & m1) != 0u, u2 = (upd & m2) != 0u;
         const int cell = (lane << 5) + c;
         const uint32_t q0 = fkey(f0n), q1 = fkey(f1n), q2 = fkey(f2n);
-        if (u0) { sGH[cell - 1].x = g2; S.key[cell - 1] = q0; S.par[cell - 1] = uint16_t(ind); }   // :238, :246-249
-        if (u1) { sGH[cell].x = g2;     S.key[cell] = q1;     S.par[cell] = uint16_t(ind); }
-        if (u2) { sGH[cell + 1].x = g2; S.key[cell + 1] = q2; S.par[cell + 1] = uint16_t(ind); }
+        const int off = (dr << 5) - 1;                      // (this row, column c-1) minus the selected cell
+        if (u0) { sGH[cell - 1].x = g2; S.key[cell - 1] = q0; S.par[cell - 1] = int8_t(off); }       // :238, :246-249
+        if (u1) { sGH[cell].x = g2;     S.key[cell] = q1;     S.par[cell] = int8_t(off + 1); }
+        if (u2) { sGH[cell + 1].x = g2; S.key[cell + 1] = q2; S.par[cell + 1] = int8_t(off + 2); }
         if (kBwd) {
             if (u0) sV[cell - 1] = expf(__fdiv_rn(-f0n, a.sqrt_w));   // :207
             if (u1) sV[cell] = expf(__fdiv_rn(-f1n, a.sqrt_w));
@@ -358,12 +358,14 @@ __global__ void __launch_bounds__(32) astar_warp32_kernel(const W32Args a) {
     uint32_t path = 0u;
     {
         if (lane == gy) path |= 1u << gx;
-        int loc = S.par[goal_rc];
+        // the start's parent is the goal in the reference (the initial value); the walk stops at the start
+        // before following it, which marks the same cells (App. A.3)
+        int loc = goal_rc - S.par[goal_rc];
         const int hops = (t_solve >= 0) ? N : (p.T - 1);
         for (int k = 0; k < hops; ++k) {
             if (lane == (loc >> 5)) path |= 1u << (loc & 31);
-            if (loc == start_rc || loc == goal_rc) break;   // reached the start (or a self-loop)
-            loc = S.par[loc];
+            if (loc == start_rc || loc == goal_rc) break;   // reached the start (or the goal's self link)
+            loc -= S.par[loc];
         }
     }
 
