@@ -40,6 +40,13 @@ enum {
 #define NASTAR_TS_EXHAUSTED (-2) /* open list ran empty: goal unreachable (the reference
                                     produces NaN -> IndexError here) */
 
+/* nastar_fwd_params.flags */
+#define NASTAR_FWD_NO_EARLY_EXIT 1 /* run exactly T steps per map: a solved map keeps stepping (re-selecting its
+                                      goal, or other nodes when g_ratio < 0.5) like the reference's batch-synchronous
+                                      loop does until the slowest map is solved (differentiable_astar.py:251-252).
+                                      Per-map early exit is exact for g_ratio >= 0.5; the host
+                                      side uses this flag to reproduce the batch coupling for g_ratio < 0.5 */
+
 typedef struct nastar_fwd_params {
     /* inputs — differentiable_astar.py:150-157 (cost_maps, start_maps, goal_maps, obstacles_maps) */
     const float *cost;   int64_t cost_stride;
@@ -53,6 +60,8 @@ typedef struct nastar_fwd_params {
     float one_minus_g_ratio;
     /* loop bound int(Tmax_eff * W * W), differentiable_astar.py:200-202 */
     int32_t T;
+    /* NASTAR_FWD_* flags */
+    int32_t flags;
     /* outputs */
     float   *histories;  /* [B][H*W] fp32 in {0,1}   — AstarOutput.histories, :265 */
     int64_t *paths;      /* [B][H*W] int64 in {0,1}  — AstarOutput.paths (backtrack, :96-125) */

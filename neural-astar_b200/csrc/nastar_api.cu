@@ -118,10 +118,14 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         if (he != cudaSuccess) return cuda_fail(he);
         nastar::W32Args a{};
         a.f = *p;
-        if (p->trace)
-            nastar::astar_warp32_kernel<true, false><<<p->B, 32, 0, stream>>>(a);
-        else
-            nastar::astar_warp32_kernel<false, false><<<p->B, 32, 0, stream>>>(a);
+        const bool noexit = (p->flags & NASTAR_FWD_NO_EARLY_EXIT) != 0;
+        if (p->trace) {
+            if (noexit) nastar::astar_warp32_kernel<true, false, true><<<p->B, 32, 0, stream>>>(a);
+            else nastar::astar_warp32_kernel<true, false, false><<<p->B, 32, 0, stream>>>(a);
+        } else {
+            if (noexit) nastar::astar_warp32_kernel<false, false, true><<<p->B, 32, 0, stream>>>(a);
+            else nastar::astar_warp32_kernel<false, false, false><<<p->B, 32, 0, stream>>>(a);
+        }
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
         const nastar::GenericLayout L(p->H, p->W);
@@ -140,9 +144,15 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
             kernel<<<grid, 32, smem, stream>>>(ga);
             return cudaSuccess;
         };
+        const bool noexit = (p->flags & NASTAR_FWD_NO_EARLY_EXIT) != 0;
         cudaError_t e;
-        if (global) e = p->trace ? launch(nastar::astar_generic_kernel<true, true, false>) : launch(nastar::astar_generic_kernel<true, false, false>);
-        else e = p->trace ? launch(nastar::astar_generic_kernel<false, true, false>) : launch(nastar::astar_generic_kernel<false, false, false>);
+        if (noexit) {
+            if (global) e = p->trace ? launch(nastar::astar_generic_kernel<true, true, false, true>) : launch(nastar::astar_generic_kernel<true, false, false, true>);
+            else e = p->trace ? launch(nastar::astar_generic_kernel<false, true, false, true>) : launch(nastar::astar_generic_kernel<false, false, false, true>);
+        } else {
+            if (global) e = p->trace ? launch(nastar::astar_generic_kernel<true, true, false>) : launch(nastar::astar_generic_kernel<true, false, false>);
+            else e = p->trace ? launch(nastar::astar_generic_kernel<false, true, false>) : launch(nastar::astar_generic_kernel<false, false, false>);
+        }
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }

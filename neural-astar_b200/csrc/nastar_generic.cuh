@@ -58,8 +58,10 @@ __device__ __forceinline__ float gen_warp_sum(float v) {
 // kBwd = true replays the search for *T_batch steps and accumulates the closed-form gradient
 //  with a dense softmax pass per step over two fp32 planes (v, acc) kept in the
 // per-CTA workspace slot (L2 resident).  Functional, not yet tuned: O(N/32) per step.
-template <bool kGlobal, bool kTrace, bool kBwd>
+// kNoExit (forward only): NASTAR_FWD_NO_EARLY_EXIT — keep stepping after the solve step, exactly T steps.
+template <bool kGlobal, bool kTrace, bool kBwd, bool kNoExit = false>
 __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
+    constexpr bool kContinue = kBwd || kNoExit;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const nastar_fwd_params& p = a.f;
     const int lane = threadIdx.x;
@@ -318,7 +320,8 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
                 key = fkey(fn);
                 if (kBwd) V[n] = expf(__fdiv_rn(-fn, a.sqrt_w));
             }
-            if (!kBwd && solved) { t_solve = t; break; }
+            if (solved && t_solve < 0) t_solve = t;
+            if (!kContinue && solved) break;
             // per-row minimum of the freshly written keys: lanes {0,1,2} {3,4,5} {6,7,8}
             const uint32_t k1 = __shfl_down_sync(kFull, key, 1), k2 = __shfl_down_sync(kFull, key, 2);
             const int x1 = __shfl_down_sync(kFull, x, 1), x2 = __shfl_down_sync(kFull, x, 2);

@@ -66,8 +66,10 @@ struct __align__(16) W32Smem {
     unsigned long long bar;    // mbarrier for the TMA prologue
 };
 
-template <bool kTrace, bool kBwd>
+// kNoExit (forward only): NASTAR_FWD_NO_EARLY_EXIT — keep stepping after the solve step, exactly T steps.
+template <bool kTrace, bool kBwd, bool kNoExit = false>
 __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
+    constexpr bool kContinue = kBwd || kNoExit;   // the loop does not stop at the solve step
     __shared__ W32Smem S;
     extern __shared__ __align__(16) float sV[];  // backward only: v = exp(-f/sqrt(W)) of open cells, else 0
     const nastar_fwd_params& p = a.f;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         const uint32_t m0 = m1 >> 1, m2 = m1 << 1;          // they fall off the row at c == 0 / 31
         // -- rescan inputs for row r (pre-expansion open cells minus the selected one); stale f
         //    values of cells relaxed this step are upper bounds and the fresh keys are merged below
-        const uint32_t open_r = (kBwd && solved) ? S.open_row[r] : (S.open_row[r] & ~m1);
+        const uint32_t open_r = (kContinue && solved) ? S.open_row[r] : (S.open_row[r] & ~m1);
         const uint32_t krs = S.key[(r << 5) + lane];
         const uint32_t rs_key = ((open_r >> lane) & 1u) ? krs : kKeyInf;
         // -- expansion inputs ----------------------------------------------------------------
@@ -317,7 +319,8 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         if (k1 < bk) { bk = k1; bc = c; }
         if (k2 < bk) { bk = k2; bc = c + 1; }
         if ((bk < rm_key) | ((bk == rm_key) & (bc < rm_col))) { rm_key = bk; rm_col = bc; }
-        if (!kBwd && solved) { t_solve = t; break; }        // :251-252 (per-map early exit, App. A.4)
+        if (solved && t_solve < 0) t_solve = t;             // first step at which the goal was selected
+        if (!kContinue && solved) break;                    // :251-252 (per-map early exit, App. A.4)
         if (near) S.open_row[lane] = open;
         // -- fold the rescan into lane r's cached minimum -------------------------------------
         const uint32_t mr = __reduce_min_sync(kFull, rs_key);
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     }
     __syncwarp();
     // selection steps executed: t on exhaustion / cap, t+1 when the loop left through the solve step
-    const int steps = (t_solve >= 0) ? (t + 1) : t;
+    const int steps = (!kContinue && t_solve >= 0) ? (t + 1) : t;
 
     if (kBwd) {
         // dL/dcost = -(1-g_ratio)/sqrt(W) * acc   (h = heuristic + cost, f = g_ratio*g + (1-g_ratio)*h)

@@ -34,7 +34,7 @@ class FwdParams(ctypes.Structure):
         ("obst", ctypes.c_void_p), ("obst_stride", ctypes.c_int64),
         ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
         ("g_ratio", ctypes.c_float), ("one_minus_g_ratio", ctypes.c_float),
-        ("T", ctypes.c_int32),
+        ("T", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("histories", ctypes.c_void_p), ("paths", ctypes.c_void_p),
         ("t_solve", ctypes.c_void_p), ("n_steps", ctypes.c_void_p), ("trace", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
@@ -143,8 +143,11 @@ def launch_count() -> int:
     return int(lib().nastar_b200_launch_count())
 
 
+FWD_NO_EARLY_EXIT = 1
+
+
 def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: torch.Tensor,
-            g_ratio: float, T: int, want_trace: bool = False):
+            g_ratio: float, T: int, want_trace: bool = False, no_early_exit: bool = False):
     """Run the search for a batch of [B,C,H,W] fp32 CUDA planes (channel 0 is used).
 
     Returns (histories [B,1,H,W] f32, paths [B,1,H,W] i64, t_solve [B] i32, n_steps [B] i32,
@@ -174,6 +177,7 @@ def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: t
     p.B, p.H, p.W = B, H, W
     p.g_ratio, p.one_minus_g_ratio = gr, omg
     p.T = int(T)
+    p.flags = FWD_NO_EARLY_EXIT if no_early_exit else 0
     with torch.cuda.device(dev):
         hist = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
         paths = torch.empty((B, 1, H, W), dtype=torch.int64, device=dev)

@@ -48,11 +48,12 @@ class _AstarSearch(torch.autograd.Function):
     """forward: libnastar_b200 search; backward: closed-form dL/dcost kernel."""
 
     @staticmethod
-    def forward(ctx, cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, want_trace):
+    def forward(ctx, cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, want_trace, no_early_exit=False):
         hist, paths, t_solve, n_steps, trace = _native.forward(
-            cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, want_trace)
+            cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, want_trace, no_early_exit)
         ctx.g_ratio = g_ratio
         ctx.T = T
+        ctx.no_early_exit = no_early_exit
         ctx.save_for_backward(cost_maps, start_maps, goal_maps, obstacles_maps, t_solve, n_steps)
         ctx.mark_non_differentiable(paths, t_solve, n_steps)
         if trace is not None:
@@ -64,13 +65,16 @@ class _AstarSearch(torch.autograd.Function):
         cost, start, goal, obst, t_solve, n_steps = ctx.saved_tensors
         grad_cost = None
         if ctx.needs_input_grad[0]:
-            T_batch = _native.batch_steps(t_solve, n_steps, ctx.T)
+            if ctx.no_early_exit:   # the forward already ran exactly the reference's T_batch steps
+                T_batch = torch.full((1,), ctx.T, dtype=torch.int32, device=cost.device)
+            else:
+                T_batch = _native.batch_steps(t_solve, n_steps, ctx.T)
             grad_cost = _native.backward(cost, start, goal, obst, grad_hist.contiguous(), T_batch, t_solve, ctx.g_ratio)
             if grad_cost.shape != cost.shape:  # cost had extra channels: only channel 0 is searched (:177)
                 full = torch.zeros_like(cost)
                 full[:, :1] = grad_cost
                 grad_cost = full
-        return grad_cost, None, None, None, None, None, None
+        return grad_cost, None, None, None, None, None, None, None
 
 
 class DifferentiableAstar(nn.Module):
@@ -114,17 +118,38 @@ class DifferentiableAstar(nn.Module):
         T = self.num_steps(cost_maps.shape[-1])
         if T < 1:
             raise ValueError("Tmax * W * W < 1: the reference loop would not execute (:203)")
+        g_ratio = float(self.g_ratio)
+        coupled = g_ratio < 0.5 and cost_maps.shape[0] > 1
+        if coupled:
+            # For g_ratio < 0.5 a solved map does not necessarily keep re-selecting its goal,
+            # so the reference's batch-synchronous loop (:251-252) changes the outputs of already-solved maps.
+            # Reproduce it: step every map without early exit, find the first step at which ALL maps select
+            # their goal, and take the state after exactly that many steps.  (One host sync; the reference
+            # synchronises every step.)
+            T = _coupled_steps(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T)
         hist, paths, t_solve, n_steps, trace = _AstarSearch.apply(
-            cost_maps, start_maps, goal_maps, obstacles_maps, float(self.g_ratio), T,
-            bool(store_intermediate_results))
+            cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, bool(store_intermediate_results), coupled)
 
         intermediate_results: List[dict] = []
         if store_intermediate_results:
-            intermediate_results = _materialise_frames(hist, paths, goal_maps, t_solve, n_steps, trace, T)
+            intermediate_results = _materialise_frames(hist, paths, goal_maps, t_solve, n_steps, trace, T,
+                                                       T_batch=T if coupled else None)
         return AstarOutput(hist, paths, intermediate_results)
 
 
-def _materialise_frames(hist, paths, goal_maps, t_solve, n_steps, trace, T) -> List[dict]:
+def _coupled_steps(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio: float, T: int) -> int:
+    """Number of iterations the reference's loop executes when solved maps keep evolving (g_ratio < 0.5)."""
+    with torch.no_grad():
+        _, _, _, _, trace = _native.forward(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T,
+                                            want_trace=True, no_early_exit=True)
+        B = goal_maps.shape[0]
+        goal_idx = goal_maps[:, 0].reshape(B, -1).argmax(-1).to(trace.dtype)
+        all_at_goal = (trace == goal_idx[:, None]).all(0)
+        first = torch.where(all_at_goal.any(), all_at_goal.float().argmax() + 1, torch.tensor(T, device=trace.device))
+    return int(first.item())
+
+
+def _materialise_frames(hist, paths, goal_maps, t_solve, n_steps, trace, T, T_batch=None) -> List[dict]:
     """Rebuild the reference's per-step frames (:210-216, :257-263) from the selection trace.
 
     Frame t holds the closed set BEFORE step t and the node selected AT step t; the reference keeps
@@ -133,7 +158,8 @@ def _materialise_frames(hist, paths, goal_maps, t_solve, n_steps, trace, T) -> L
     """
     B, _, H, W = hist.shape
     N = H * W
-    T_batch = int(_native.batch_steps(t_solve, n_steps, T).item())
+    if T_batch is None:
+        T_batch = int(_native.batch_steps(t_solve, n_steps, T).item())
     goal_idx = goal_maps[:, 0].reshape(B, -1).argmax(-1)
     tr = trace[:, :T_batch].to(torch.int64)
     tr = torch.where(tr < 0, goal_idx[:, None].expand_as(tr), tr)

@@ -181,31 +181,47 @@ int nastar_oracle_forward_literal(const float *cost, const float *start, const f
         memcpy(m->open, start + (size_t)b * N, sizeof(float) * N);       /* :187 */
         for (int i = 0; i < N; ++i) m->parents[i] = (float)m->goal;      /* :195-198 */
     }
-    /* The reference runs one loop over t for the whole batch and stops when every map is solved
-     * (:251-252).  Maps only interact through that stop condition, so the same result is obtained
-     * without a barrier per step: phase 1 runs each map to its own solve step, T_batch is the
-     * maximum, phase 2 replays the post-solve iterations each map would still have executed. */
-    int32_t *done = (int32_t *)calloc((size_t)B, sizeof(int32_t));
-#pragma omp parallel for schedule(dynamic, 1)
-    for (int b = 0; b < B; ++b) {
-        int t = 0;
-        for (t = 0; t < T; ++t) {
-            int uns = literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N, goal + (size_t)b * N,
-                                   H, W, g_ratio, one_minus_g_ratio, sqrt_w, t,
-                                   trace ? trace + (size_t)b * T + t : NULL);
-            if (!uns) { ++t; break; }
-        }
-        done[b] = t; /* iterations executed so far */
-    }
     int tb = 0;
-    for (int b = 0; b < B; ++b) if (done[b] > tb) tb = done[b];
+    if (g_ratio >= 0.5f) {
+        /* The reference runs one loop over t for the whole batch and stops when every map is solved
+         * (:251-252).  For g_ratio >= 0.5 a solved map keeps re-selecting its goal, so
+         * maps only interact through the stop step: phase 1 runs each map to its own solve step, T_batch
+         * is the maximum, phase 2 replays the post-solve iterations each map would still have executed.
+         * (No barrier per step: needed for sane OpenMP scaling of the CPU baseline.) */
+        int32_t *done = (int32_t *)calloc((size_t)B, sizeof(int32_t));
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int b = 0; b < B; ++b) {
-        for (int t = done[b]; t < tb; ++t)
-            literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N, goal + (size_t)b * N, H, W,
-                         g_ratio, one_minus_g_ratio, sqrt_w, t, trace ? trace + (size_t)b * T + t : NULL);
+        for (int b = 0; b < B; ++b) {
+            int t = 0;
+            for (t = 0; t < T; ++t) {
+                int uns = literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N, goal + (size_t)b * N,
+                                       H, W, g_ratio, one_minus_g_ratio, sqrt_w, t,
+                                       trace ? trace + (size_t)b * T + t : NULL);
+                if (!uns) { ++t; break; }
+            }
+            done[b] = t; /* iterations executed so far */
+        }
+        for (int b = 0; b < B; ++b) if (done[b] > tb) tb = done[b];
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int b = 0; b < B; ++b) {
+            for (int t = done[b]; t < tb; ++t)
+                literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N, goal + (size_t)b * N, H, W,
+                             g_ratio, one_minus_g_ratio, sqrt_w, t, trace ? trace + (size_t)b * T + t : NULL);
+        }
+        free(done);
+    } else {
+        /* g_ratio < 0.5: a solved map may select other nodes again, so the loop is run in lock step and
+         * stops at the first iteration in which EVERY map selects its goal (:219-220, :251-252). */
+        for (int t = 0; t < T; ++t) {
+            int any_unsolved = 0;
+#pragma omp parallel for schedule(static) reduction(| : any_unsolved)
+            for (int b = 0; b < B; ++b)
+                any_unsolved |= literal_step(&maps[b], cost + (size_t)b * N, obst + (size_t)b * N,
+                                             goal + (size_t)b * N, H, W, g_ratio, one_minus_g_ratio, sqrt_w, t,
+                                             trace ? trace + (size_t)b * T + t : NULL);
+            tb = t + 1;
+            if (!any_unsolved) break;
+        }
     }
-    free(done);
     const int last_t = tb - 1;
     for (int b = 0; b < B; ++b) {
         memcpy(hist + (size_t)b * N, maps[b].hist, sizeof(float) * N);
@@ -271,7 +287,7 @@ static void spec_expand(spec_map_t *m, const float *cost, const float *obst, int
  */
 int nastar_oracle_forward_spec(const float *cost, const float *start, const float *goal,
                                const float *obst, int B, int H, int W, float g_ratio,
-                               float one_minus_g_ratio, int T, float *hist, int64_t *paths,
+                               float one_minus_g_ratio, int T, int no_early_exit, float *hist, int64_t *paths,
                                int32_t *t_solve, int32_t *n_steps, int32_t *trace)
 {
     if (B <= 0 || H <= 0 || W <= 0 || T <= 0) return NASTAR_ORACLE_EINVAL;
@@ -299,7 +315,8 @@ int nastar_oracle_forward_spec(const float *cost, const float *start, const floa
             m.closed[ind] = 1;
             if (ind != gi) m.open[ind] = 0;       /* the goal, once selected, stays open */
             spec_expand(&m, cb, ob, H, W, ind);
-            if (ind == gi) { ts = t; break; }
+            if (ind == gi && ts < 0) ts = t;
+            if (ind == gi && !no_early_exit) break;   /* no_early_exit: exactly T steps, like the batch loop */
         }
         float *hb = hist + (size_t)b * N;
         int64_t *pb = paths + (size_t)b * N;

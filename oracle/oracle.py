@@ -42,7 +42,7 @@ def _load():
                                                       fp, lp, ip, ip, ip]
         lib.nastar_oracle_forward_literal.restype = ctypes.c_int
         lib.nastar_oracle_forward_spec.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                   ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                   ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                                    fp, lp, ip, ip, ip]
         lib.nastar_oracle_forward_spec.restype = ctypes.c_int
         lib.nastar_oracle_backward.argtypes = [fp, fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -85,11 +85,11 @@ def num_steps(Tmax: float, training: bool, W: int) -> int:
 
 
 def forward(cost, start, goal, obst, g_ratio=0.5, Tmax=1.0, training=False, mode="spec",
-            want_trace=False) -> OracleOutput:
+            want_trace=False, T=None, no_early_exit=False) -> OracleOutput:
     lib = _load()
     c, s, g, o = _planes(cost), _planes(start), _planes(goal), _planes(obst)
     B, H, W = c.shape
-    T = num_steps(Tmax, training, W)
+    T = int(T) if T is not None else num_steps(Tmax, training, W)
     gr, omg, sq = scalars(g_ratio, W)
     hist = np.zeros((B, H, W), np.float32)
     paths = np.zeros((B, H, W), np.int64)
@@ -107,7 +107,7 @@ def forward(cost, start, goal, obst, g_ratio=0.5, Tmax=1.0, training=False, mode
         ns[:] = T_batch
     elif mode == "spec":
         rc = lib.nastar_oracle_forward_spec(_p(c, ctypes.c_float), _p(s, ctypes.c_float), _p(g, ctypes.c_float),
-                                            _p(o, ctypes.c_float), B, H, W, gr, omg, T,
+                                            _p(o, ctypes.c_float), B, H, W, gr, omg, T, int(bool(no_early_exit)),
                                             _p(hist, ctypes.c_float), _p(paths, ctypes.c_int64),
                                             _p(ts, ctypes.c_int32), _p(ns, ctypes.c_int32), tp)
         T_batch = int(ns.max())

@@ -14,7 +14,24 @@ from golden_util import Golden, all_names
 NAMES = all_names()
 
 
+def spec_batch_coupled(oracle, g):
+    """SPEC form of the reference's batch-synchronous loop for g_ratio < 0.5 (the procedure the product's host
+    side runs): step every map without early exit, find the first step at which ALL maps select their goal
+    (differentiable_astar.py:219-220,251-252), then take the state after exactly that many steps."""
+    T = g.W * g.W
+    full = oracle.forward(g.cost, g.start, g.goal, g.obst, g_ratio=g.g_ratio, mode="spec", want_trace=True,
+                          T=T, no_early_exit=True)
+    at_goal = (full.trace == g.z["goal_idx"][:, None]).all(0)
+    T_batch = int(np.argmax(at_goal)) + 1 if at_goal.any() else T
+    o = oracle.forward(g.cost, g.start, g.goal, g.obst, g_ratio=g.g_ratio, mode="spec", want_trace=True,
+                       T=T_batch, no_early_exit=True)
+    return o, T_batch
+
+
 def _run(oracle, g, mode, **kw):
+    if mode == "spec" and g.meta.get("lowg"):
+        o, T_batch = spec_batch_coupled(oracle, g)
+        return o.histories, o.paths, T_batch
     if g.independent:
         outs = [oracle.forward(g.cost[i:i + 1], g.start[i:i + 1], g.goal[i:i + 1], g.obst[i:i + 1],
                                g_ratio=g.g_ratio, mode=mode, **kw) for i in range(g.B)]
@@ -55,6 +72,12 @@ def test_selection_trace_matches_reference(oracle, name):
     ref = g.z["trace"]  # [B, T_batch]
     lit = oracle.forward(g.cost, g.start, g.goal, g.obst, g_ratio=g.g_ratio, mode="literal", want_trace=True)
     np.testing.assert_array_equal(lit.trace[:, : ref.shape[1]], ref)
+    if g.meta.get("lowg"):
+        # batch-coupled: every step of every map is defined by the reference, post-solve steps included
+        o, T_batch = spec_batch_coupled(oracle, g)
+        assert T_batch == ref.shape[1]
+        np.testing.assert_array_equal(o.trace, ref)
+        return
     o = oracle.forward(g.cost, g.start, g.goal, g.obst, g_ratio=g.g_ratio, mode="spec", want_trace=True)
     swapped = 0
     for b in range(g.B):
