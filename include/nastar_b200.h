@@ -117,8 +117,9 @@ int nastar_b200_backward(const nastar_bwd_params *p, void *stream);
 int nastar_b200_batch_steps(const int32_t *t_solve, const int32_t *n_steps, int32_t B, int32_t T,
                             int32_t *T_batch, void *stream);
 
-/* Which engine a shape dispatches to: 1 = warp-resident (H,W <= 32), 2 = generic warp engine
- * with shared-memory state, 3 = generic with global-memory state, 0 = unsupported. */
+/* Which forward engine a shape dispatches to: 1 = warp-resident (H,W <= 32), 4 = warp-resident 64-wide
+ * (H,W <= 64), 2 = generic warp engine with shared-memory state, 3 = generic with global-memory state,
+ * 0 = unsupported.  (The backward of engine-4 shapes runs on the generic engine.) */
 int nastar_b200_engine_for(int32_t H, int32_t W);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */

@@ -7,6 +7,7 @@
 #include "../../include/nastar_b200.h"
 #include "nastar_generic.cuh"
 #include "nastar_warp32.cuh"
+#include "nastar_warp64.cuh"
 
 namespace {
 std::atomic<uint64_t> g_launches{0};
@@ -42,6 +43,32 @@ cudaError_t ensure_heur32(cudaStream_t stream) {
     done_mask.fetch_or(bit, std::memory_order_release);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaSuccess;
+}
+
+cudaError_t ensure_heur64(cudaStream_t stream) {
+    static std::atomic<uint64_t> done_mask{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = uint64_t(1) << (dev & 63);
+    if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    nastar::heur64_init_kernel<<<16, 256, 0, stream>>>();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return e;
+    done_mask.fetch_or(bit, std::memory_order_release);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaSuccess;
+}
+
+// generic engine variant for a shape: 2 = state in shared memory, 3 = state in the HBM workspace, 0 = too large
+int generic_engine_for(int32_t H, int32_t W) {
+    if (H <= 0 || W <= 0 || int64_t(H) * W > (int64_t(1) << 30)) return 0;
+    const nastar::GenericLayout L(H, W);
+    if (L.smem_common() + L.smem_planes() <= kMaxDynSmem) return 2;
+    if (L.smem_common() <= kMaxDynSmem) return 3;
+    return 0;
 }
 
 int generic_slots(int B) {
@@ -85,11 +112,8 @@ int nastar_b200_abi_version(void) { return NASTAR_B200_ABI_VERSION; }
 int nastar_b200_engine_for(int32_t H, int32_t W) {
     if (H <= 0 || W <= 0) return 0;
     if (H <= 32 && W <= 32) return 1;
-    if (int64_t(H) * W > (int64_t(1) << 30)) return 0;
-    const nastar::GenericLayout L(H, W);
-    if (L.smem_common() + L.smem_planes() <= kMaxDynSmem) return 2;
-    if (L.smem_common() <= kMaxDynSmem) return 3;
-    return 0;
+    if (H <= 64 && W <= 64) return 4;   // forward; the backward of these shapes runs on the generic engine
+    return generic_engine_for(H, W);
 }
 
 size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
@@ -98,8 +122,9 @@ size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
 }
 
 size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
-    const int e = nastar_b200_engine_for(H, W);
-    if (B <= 0 || e < 2) return 0;
+    if (B <= 0 || nastar_b200_engine_for(H, W) == 1) return 0;
+    const int e = generic_engine_for(H, W);
+    if (e == 0) return 0;
     return size_t(generic_slots(B)) * nastar::GenericLayout(H, W).slot_total(e == 3, true);
 }
 
@@ -126,6 +151,22 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
             if (noexit) nastar::astar_warp32_kernel<false, false, true><<<p->B, 32, 0, stream>>>(a);
             else nastar::astar_warp32_kernel<false, false, false><<<p->B, 32, 0, stream>>>(a);
         }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (engine == 4) {
+        cudaError_t he = ensure_heur64(stream);
+        if (he != cudaSuccess) return cuda_fail(he);
+        const bool noexit = (p->flags & NASTAR_FWD_NO_EARLY_EXIT) != 0;
+        const size_t smem = sizeof(nastar::W64Smem);
+        auto launch = [&](auto kernel) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            kernel<<<p->B, 32, smem, stream>>>(*p);
+            return cudaSuccess;
+        };
+        cudaError_t e;
+        if (p->trace) e = noexit ? launch(nastar::astar_warp64_kernel<true, true>) : launch(nastar::astar_warp64_kernel<true, false>);
+        else e = noexit ? launch(nastar::astar_warp64_kernel<false, true>) : launch(nastar::astar_warp64_kernel<false, false>);
+        if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
         const nastar::GenericLayout L(p->H, p->W);
@@ -167,7 +208,8 @@ int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
         return NASTAR_EINVAL;
     if (p->B <= 0 || p->H <= 0 || p->W <= 0) return NASTAR_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    const int engine = nastar_b200_engine_for(p->H, p->W);
+    int engine = nastar_b200_engine_for(p->H, p->W);
+    if (engine != 1) engine = generic_engine_for(p->H, p->W);   // warp64 shapes: backward on the generic engine
     if (engine == 0) return NASTAR_EUNSUPPORTED;
     if (engine >= 2) {
         const nastar::GenericLayout L(p->H, p->W);

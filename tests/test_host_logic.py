@@ -68,12 +68,16 @@ def test_struct_layout_matches_ctypes(built_lib, tmp_path):
 def test_engine_dispatch_and_workspace(built_lib):
     L = built_lib.lib()
     assert L.nastar_b200_engine_for(32, 32) == 1 and L.nastar_b200_engine_for(12, 12) == 1
-    assert L.nastar_b200_engine_for(64, 64) == 2 and L.nastar_b200_engine_for(64, 128) == 2
+    assert L.nastar_b200_engine_for(64, 64) == 4 and L.nastar_b200_engine_for(33, 20) == 4
+    assert L.nastar_b200_engine_for(64, 128) == 2
     assert L.nastar_b200_engine_for(128, 128) == 2
     assert L.nastar_b200_engine_for(256, 256) == 3
     assert L.nastar_b200_engine_for(0, 5) == 0 and L.nastar_b200_engine_for(100000, 100000) == 0
     assert L.nastar_b200_forward_workspace_bytes(8, 32, 32) == 0
     assert L.nastar_b200_forward_workspace_bytes(4, 256, 256) >= 4 * 256 * 256 * 9
+    assert L.nastar_b200_forward_workspace_bytes(4, 64, 64) == 0
+    assert L.nastar_b200_backward_workspace_bytes(4, 64, 64) >= 4 * 64 * 64 * 8   # backward of 64x64: generic engine
+    assert L.nastar_b200_backward_workspace_bytes(4, 32, 32) == 0
     assert L.nastar_b200_status_string(2).decode().startswith("unsupported")
 
 
