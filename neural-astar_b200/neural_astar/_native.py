@@ -6,6 +6,7 @@ CPU or eager-PyTorch fallback for the search.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
 import os
@@ -72,6 +73,7 @@ EXPORTS = (
 )
 
 _lib = None
+_ws_cache = {}
 
 
 class NativeLibraryMissing(ImportError):
@@ -178,13 +180,16 @@ def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: t
     p.g_ratio, p.one_minus_g_ratio = gr, omg
     p.T = int(T)
     p.flags = FWD_NO_EARLY_EXIT if no_early_exit else 0
-    with torch.cuda.device(dev):
+    ws_bytes = _ws_cache.get((B, H, W))
+    if ws_bytes is None:
+        ws_bytes = _ws_cache[(B, H, W)] = int(L.nastar_b200_forward_workspace_bytes(B, H, W))
+    guard = contextlib.nullcontext() if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+    with guard:
         hist = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
         paths = torch.empty((B, 1, H, W), dtype=torch.int64, device=dev)
-        t_solve = torch.empty((B,), dtype=torch.int32, device=dev)
-        n_steps = torch.empty((B,), dtype=torch.int32, device=dev)
+        counters = torch.empty((2, B), dtype=torch.int32, device=dev)   # [t_solve | n_steps]
+        t_solve, n_steps = counters[0], counters[1]
         trace = torch.empty((B, int(T)), dtype=torch.int32, device=dev) if want_trace else None
-        ws_bytes = L.nastar_b200_forward_workspace_bytes(B, H, W)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
         p.histories, p.paths = hist.data_ptr(), paths.data_ptr()
         p.t_solve, p.n_steps = t_solve.data_ptr(), n_steps.data_ptr()
