@@ -70,7 +70,18 @@ class EncoderBase(nn.Module):
                 scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
                 w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
                 b = ((conv.bias - bn.running_mean) * scale + bn.bias).contiguous()
-            plan.append((w, b, conv.stride, conv.padding, conv.dilation, relu, pool))
+            head = None
+            if (conv.out_channels == 1 and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
+                    and conv.padding == (1, 1) and conv.dilation == (1, 1) and not relu and pool is None):
+                # single-output-channel head: cuDNN's implicit GEMM wastes a 256-wide tile on one channel
+                # (134 us at 100x256x32x32); a per-pixel [C] x [C,9] GEMM followed by a 9-tap gather is the
+                # same sum in a different order (86 us) — see _conv3x3_single_output
+                with torch.no_grad():
+                    taps = torch.zeros(1, 9, 3, 3, device=w.device, dtype=w.dtype)
+                    for k in range(9):
+                        taps[0, k, k // 3, k % 3] = 1.0
+                    head = (w[0].reshape(w.shape[1], 9).contiguous(), taps)
+            plan.append((w, b, conv.stride, conv.padding, conv.dilation, relu, pool, head))
         self._plan, self._plan_key = plan, key
         return plan
 
@@ -83,8 +94,21 @@ def _run_plan(plan, x: torch.Tensor) -> torch.Tensor:
         return _run_plan_inner(plan, x)
 
 
+def _conv3x3_single_output(x: torch.Tensor, wm: torch.Tensor, taps: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """3x3 / pad 1 convolution with ONE output channel on a channels-last activation:
+    t[n,y,x,k] = <x[n,y,x,:], w[:,k]> for the 9 taps (one skinny fp32 GEMM over the pixels), then
+    out[n,y,x] = b + sum_k t[n, y+ky-1, x+kx-1, k] (a 9->1 one-hot 3x3 convolution, kept in full fp32)."""
+    B, C, H, W = x.shape
+    t = (x.permute(0, 2, 3, 1).reshape(-1, C) @ wm).view(B, H, W, 9).permute(0, 3, 1, 2)
+    with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=False):
+        return torch.nn.functional.conv2d(t, taps, b, padding=1)
+
+
 def _run_plan_inner(plan, x: torch.Tensor) -> torch.Tensor:
-    for w, b, stride, padding, dilation, relu, pool in plan:
+    for w, b, stride, padding, dilation, relu, pool, head in plan:
+        if head is not None and x.is_contiguous(memory_format=torch.channels_last):
+            x = _conv3x3_single_output(x, head[0], head[1], b)
+            continue
         if relu:
             x = torch.cudnn_convolution_relu(x, w, b, stride, padding, dilation, 1)
         else:
