@@ -90,7 +90,13 @@ typedef struct nastar_bwd_params {
        DEVICE from *T_batch so that no host synchronisation is needed between forward
        and backward */
     const int32_t *T_batch;
-    const int32_t *t_solve;   /* [B] the forward's t_solve[] for the same inputs and loop bound */
+    const int32_t *t_solve;   /* [B] the forward's t_solve[] for the same inputs and loop bound.  Used for (a) the
+                                 stationary post-solve shortcut when g_ratio >= 0.5 and (b) the goal clamp: the
+                                 gradient at a map's goal is blocked iff 0 <= t_solve[b] < T_batch-1 (the goal is
+                                 then selected again and clamp(hist+sel) saw 2, differentiable_astar.py:222-223).
+                                 For g_ratio < 0.5 a solved map need not re-select its goal: pass 0 for maps
+                                 whose goal is selected at least twice within T_batch steps and T_batch otherwise
+                                 (the Python module derives this from a NO_EARLY_EXIT trace) */
     const float *grad_histories; int64_t grad_stride; /* dL/d histories, [B][H*W] */
     float *grad_cost;                                  /* dL/d cost_maps, [B][H*W], overwritten */
     void  *workspace;

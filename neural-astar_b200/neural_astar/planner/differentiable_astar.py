@@ -48,13 +48,21 @@ class _AstarSearch(torch.autograd.Function):
     """forward: libnastar_b200 search; backward: closed-form dL/dcost kernel."""
 
     @staticmethod
-    def forward(ctx, cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, want_trace, no_early_exit=False):
+    def forward(ctx, cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, want_trace, goal_clamped=None):
+        # goal_clamped is given only on the batch-coupled path (g_ratio < 0.5, see _coupled_steps): the search then
+        # runs exactly T steps per map and the backward is told which goals were selected more than once
+        no_early_exit = goal_clamped is not None
         hist, paths, t_solve, n_steps, trace = _native.forward(
             cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, want_trace, no_early_exit)
         ctx.g_ratio = g_ratio
         ctx.T = T
         ctx.no_early_exit = no_early_exit
-        ctx.save_for_backward(cost_maps, start_maps, goal_maps, obstacles_maps, t_solve, n_steps)
+        if no_early_exit:
+            # encoding understood by nastar_b200_backward: t_solve < T_batch-1  <=>  gradient blocked at the goal
+            t_for_bwd = torch.where(goal_clamped, torch.zeros_like(t_solve), torch.full_like(t_solve, T))
+        else:
+            t_for_bwd = t_solve
+        ctx.save_for_backward(cost_maps, start_maps, goal_maps, obstacles_maps, t_for_bwd, n_steps)
         ctx.mark_non_differentiable(paths, t_solve, n_steps)
         if trace is not None:
             ctx.mark_non_differentiable(trace)
@@ -120,15 +128,16 @@ class DifferentiableAstar(nn.Module):
             raise ValueError("Tmax * W * W < 1: the reference loop would not execute (:203)")
         g_ratio = float(self.g_ratio)
         coupled = g_ratio < 0.5 and cost_maps.shape[0] > 1
+        goal_clamped = None
         if coupled:
             # For g_ratio < 0.5 a solved map does not necessarily keep re-selecting its goal,
             # so the reference's batch-synchronous loop (:251-252) changes the outputs of already-solved maps.
             # Reproduce it: step every map without early exit, find the first step at which ALL maps select
             # their goal, and take the state after exactly that many steps.  (One host sync; the reference
             # synchronises every step.)
-            T = _coupled_steps(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T)
+            T, goal_clamped = _coupled_steps(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T)
         hist, paths, t_solve, n_steps, trace = _AstarSearch.apply(
-            cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, bool(store_intermediate_results), coupled)
+            cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T, bool(store_intermediate_results), goal_clamped)
 
         intermediate_results: List[dict] = []
         if store_intermediate_results:
@@ -137,16 +146,21 @@ class DifferentiableAstar(nn.Module):
         return AstarOutput(hist, paths, intermediate_results)
 
 
-def _coupled_steps(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio: float, T: int) -> int:
-    """Number of iterations the reference's loop executes when solved maps keep evolving (g_ratio < 0.5)."""
+def _coupled_steps(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio: float, T: int):
+    """(T_batch, goal_clamped[B]) for g_ratio < 0.5: the number of iterations the reference's loop executes when
+    solved maps keep evolving, and per map whether its goal is selected more than once within them — then
+    clamp(hist + sel) saw 2 at the goal and blocks its gradient (differentiable_astar.py:222-223)."""
     with torch.no_grad():
         _, _, _, _, trace = _native.forward(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio, T,
                                             want_trace=True, no_early_exit=True)
         B = goal_maps.shape[0]
         goal_idx = goal_maps[:, 0].reshape(B, -1).argmax(-1).to(trace.dtype)
-        all_at_goal = (trace == goal_idx[:, None]).all(0)
+        at_goal = trace == goal_idx[:, None]
+        all_at_goal = at_goal.all(0)
         first = torch.where(all_at_goal.any(), all_at_goal.float().argmax() + 1, torch.tensor(T, device=trace.device))
-    return int(first.item())
+        T_batch = int(first.item())
+        goal_clamped = at_goal[:, :T_batch].sum(1) >= 2
+    return T_batch, goal_clamped
 
 
 def _materialise_frames(hist, paths, goal_maps, t_solve, n_steps, trace, T, T_batch=None) -> List[dict]:

@@ -24,9 +24,13 @@ def main():
             r1 = mg.run_search(cst[b:b+1], starts[b:b+1], goals[b:b+1], maps[b:b+1], g_ratio=gr)
             diff += int((r1["hist"] != res["hist"][b:b+1]).sum())
         print(tag, "T_batch", res["T_batch"], "hist cells differing from per-map exit:", diff)
+        a = mg.common_arrays(maps, starts, goals, res, cost=cst)
+        gen = torch.Generator().manual_seed(11)
+        G = torch.randn(cst.shape, generator=gen)
+        rg = mg.run_search(cst, starts, goals, maps, g_ratio=gr, grad_hist=G)   # reference autograd through the coupled loop
+        a.update(rand_G=G[:, 0].numpy(), rand_grad_cost=rg["grad_cost"][:, 0].numpy())
         mg.save(f"mazes032_lowg_{tag}", dict(desc=f"mazes_032 test[:16], learned costs, g_ratio={gr}, batch-coupled (B=16)",
-                                             g_ratio=gr, vanilla=False, lowg=True),
-                **mg.common_arrays(maps, starts, goals, res, cost=cst))
+                                             g_ratio=gr, vanilla=False, lowg=True), **a)
 
 if __name__ == "__main__":
     main()

@@ -154,3 +154,18 @@ def test_generic_engine_backward_vs_oracle(native, oracle, H, W, B):
         want = oracle.backward(cost, start, goal, obst, G, Tb, g_ratio=0.5)
         assert np.isfinite(gc).all()
         assert _relerr(gc, want) < TOL, (H, W, Tmax)
+
+
+@pytest.mark.parametrize("name", ["mazes032_lowg_gr00_cost10", "mazes032_lowg_gr02", "mazes032_lowg_gr04_cost10"])
+def test_low_g_ratio_coupled_backward_vs_reference_autograd(name):
+    """g_ratio < 0.5, B > 1: gradient through the batch-coupled loop (post-solve steps that select non-goal nodes,
+    exact goal-clamp detection) vs the reference's autograd."""
+    from neural_astar.planner.differentiable_astar import DifferentiableAstar
+
+    g = Golden(name)
+    astar = DifferentiableAstar(g_ratio=g.g_ratio).cuda().eval()
+    cost = _dev(g.cost).requires_grad_(True)
+    out = astar(cost, _dev(g.start), _dev(g.goal), _dev(g.obst))
+    np.testing.assert_array_equal(out.histories.detach().cpu().numpy() != 0, g.bits("hist_bits") != 0)
+    (out.histories * _dev(g.plane("rand_G").astype(np.float32))).sum().backward()
+    assert _relerr(cost.grad.cpu().numpy(), g.plane("rand_grad_cost")) < TOL

@@ -122,6 +122,9 @@ def test_backward_l1_training_grad(oracle):
 
 
 @pytest.mark.parametrize("name,T_key,G_key,out_key", [
+    ("mazes032_lowg_gr00_cost10", "T_batch", "rand_G", "rand_grad_cost"),   # g_ratio < 0.5: post-solve steps matter
+    ("mazes032_lowg_gr02", "T_batch", "rand_G", "rand_grad_cost"),
+    ("mazes032_lowg_gr04_cost10", "T_batch", "rand_G", "rand_grad_cost"),
     ("mazes032_neural_test", "T_batch", "rand_G", "rand_grad_cost"),
     ("warcraft12_synth", "T_batch", "rand_G", "rand_grad_cost"),
     ("warcraft12_synth", "train_T_batch", "rand_G", "train_grad_cost"),
