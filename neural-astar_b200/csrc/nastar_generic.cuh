@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             // 128-bit loads, kUnroll segments of 128 cells in flight per plane (the prologue is a pure
             // HBM stream; with one warp per map the only way to cover DRAM latency is load-level parallelism)
             constexpr int kUnroll = 8;
-            const int nseg = N >> 7;
+            const int nseg = (N + 127) >> 7;   // the last segment may be partial (N is a multiple of 32, not of 128)
+            const int nq = N >> 2;             // float4 count of a plane
             const float4* o4 = reinterpret_cast<const float4*>(gObst);
             const float4* s4 = reinterpret_cast<const float4*>(gStart);
             const float4* g4 = reinterpret_cast<const float4*>(gGoal);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
                     const int q = ((seg0 + u) << 5) + lane;
-                    const bool in = (seg0 + u) < nseg;
+                    const bool in = q < nq;
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                     vo[u] = in ? __ldg(o4 + q) : z;
                     vs[u] = in ? __ldg(s4 + q) : z;
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
                         word |= __shfl_xor_sync(kFull, word, 1);
                         word |= __shfl_xor_sync(kFull, word, 2);
                         word |= __shfl_xor_sync(kFull, word, 4);
-                        if ((lane & 7) == 0) sPass[((seg0 + u) << 2) + (lane >> 3)] = word;
+                        if ((lane & 7) == 0 && ((seg0 + u) << 2) + (lane >> 3) < L.nbits)
+                            sPass[((seg0 + u) << 2) + (lane >> 3)] = word;
                         const bool hs = (vs[u].x != 0.f) | (vs[u].y != 0.f) | (vs[u].z != 0.f) | (vs[u].w != 0.f);
                         const bool hg = (vg[u].x != 0.f) | (vg[u].y != 0.f) | (vg[u].z != 0.f) | (vg[u].w != 0.f);
                         const uint32_t bs = __ballot_sync(kFull, hs), bg = __ballot_sync(kFull, hg);
@@ -388,12 +390,14 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         if (((W & 31) == 0) && aligned16(gHist) && aligned16(gPath)) {
             // flat bit index == row-word index: each lane expands 4 cells per segment into one 128-bit
             // histories store and two 128-bit paths stores (fully coalesced)
-            const int nseg = N >> 7;
+            const int nseg = (N + 127) >> 7;
+            const int nq = N >> 2;
             const int sh = (lane & 7) << 2;
             for (int seg = 0; seg < nseg; ++seg) {
                 const int wi = (seg << 2) + (lane >> 3);
-                const uint32_t cb = sClosed[wi] >> sh, pb = sPath[wi] >> sh;
                 const int q = (seg << 5) + lane;
+                if (q >= nq) continue;            // partial last segment
+                const uint32_t cb = sClosed[wi] >> sh, pb = sPath[wi] >> sh;
                 reinterpret_cast<float4*>(gHist)[q] = make_float4((cb & 1u) ? 1.f : 0.f, (cb & 2u) ? 1.f : 0.f,
                                                                   (cb & 4u) ? 1.f : 0.f, (cb & 8u) ? 1.f : 0.f);
                 reinterpret_cast<longlong2*>(gPath)[2 * q] = make_longlong2((pb & 1u) ? 1ll : 0ll, (pb & 2u) ? 1ll : 0ll);

@@ -131,7 +131,7 @@ def test_module_api_backward_reaches_encoder(native, oracle):
     assert _relerr(cost.grad.cpu().numpy(), want) < TOL
 
 
-@pytest.mark.parametrize("H,W,B", [(64, 64, 6), (40, 48, 5), (33, 70, 4), (144, 136, 2)])
+@pytest.mark.parametrize("H,W,B", [(64, 64, 6), (40, 48, 5), (33, 70, 4), (144, 136, 2), (33, 64, 4), (65, 96, 2)])
 def test_generic_engine_backward_vs_oracle(native, oracle, H, W, B):
     """Backward for maps larger than 32x32 (engine 2: smem state; engine 3: HBM workspace)."""
     rng = np.random.RandomState(H * 7 + W)

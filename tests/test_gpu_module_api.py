@@ -126,7 +126,7 @@ def test_neural_astar_with_reference_checkpoint_quality():
     np.testing.assert_array_equal(o2.paths.cpu().numpy() != 0, gn.bits("path_bits") != 0)
 
 
-@pytest.mark.parametrize("H,W,B", [(128, 128, 6), (96, 160, 4), (256, 256, 4), (200, 300, 3)])
+@pytest.mark.parametrize("H,W,B", [(128, 128, 6), (96, 160, 4), (256, 256, 4), (200, 300, 3), (65, 96, 3), (67, 160, 2)])
 def test_large_maps_vs_oracle(oracle, H, W, B):
     """Engine 2 (shared-memory state, up to 128x128) and engine 3 (HBM workspace, e.g. 256x256 = Config 5)."""
     from neural_astar import _native
