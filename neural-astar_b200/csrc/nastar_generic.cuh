@@ -31,8 +31,8 @@ struct GenericLayout {
     __host__ __device__ size_t smem_planes() const { return size_t(npad()) * 13; }
     // per-CTA workspace slot of the kGlobal variant: g, f (fp32) + parent (u8)
     __host__ __device__ size_t slot_bytes() const { return (size_t(npad()) * 9 + 255) & ~size_t(255); }
-    // backward adds two fp32 planes (v, acc) per slot, always in the workspace
-    __host__ __device__ size_t bwd_bytes() const { return (size_t(npad()) * 8 + 255) & ~size_t(255); }
+    // backward adds a fp32 plane (v) and a fp64 plane (acc) per slot, always in the workspace
+    __host__ __device__ size_t bwd_bytes() const { return (size_t(npad()) * 12 + 255) & ~size_t(255); }
     __host__ __device__ size_t slot_total(bool global_state, bool bwd) const {
         return (global_state ? slot_bytes() : 0) + (bwd ? bwd_bytes() : 0);
     }
@@ -86,13 +86,13 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         F = G + np;
         Par = reinterpret_cast<uint8_t*>(F + np);
     }
-    float* V = nullptr;    // backward: v = exp(-f/sqrt(W)) of open cells, else 0
-    float* ACC = nullptr;  // backward: sum_t y_t[p] * (Gh[p] - <Gh, y_t>)
+    float* V = nullptr;     // backward: v = exp(-f/sqrt(W)) of open cells, else 0
+    double* ACC = nullptr;  // backward: sum_t y_t[p] * (Gh[p] - <Gh, y_t>), fp64 (thousands of steps on big maps)
     if (kBwd) {
         unsigned char* slot = static_cast<unsigned char*>(p.workspace) + size_t(blockIdx.x) * L.slot_total(kGlobal, true) +
                               (kGlobal ? L.slot_bytes() : 0);
-        V = reinterpret_cast<float*>(slot);
-        ACC = V + np;
+        ACC = reinterpret_cast<double*>(slot);
+        V = reinterpret_cast<float*>(ACC + np);
     }
     uint32_t* sPass = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
     uint32_t* sOpen = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             ts_in = a.t_solve_in[b];
             blocked = (ts_in >= 0) && (ts_in < Tb - 1);   // goal clamp, differentiable_astar.py:222-223
             gG = a.grad_hist + int64_t(b) * a.grad_stride;
-            for (int i = lane; i < N; i += 32) { V[i] = 0.f; ACC[i] = 0.f; }
+            for (int i = lane; i < N; i += 32) { V[i] = 0.f; ACC[i] = 0.0; }
             __syncwarp();
         }
         if (start_idx >= 0 && lane == 0) {
@@ -248,23 +248,28 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             const uint32_t m = __reduce_min_sync(kFull, bk);
             if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
             if (kBwd) {
-                float s_ = 0.f, d_ = 0.f;
-                for (int i = lane; i < N; i += 32) {
-                    const float v = V[i];
-                    const float g = (blocked && i == goal_idx) ? 0.f : __ldg(gG + i);
-                    s_ += v;
-                    d_ = fmaf(g, v, d_);
-                }
-                s_ = gen_warp_sum(s_);
-                d_ = gen_warp_sum(d_);
-                const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
-                const float inv = (last ? float(Tb - t) : 1.f) / s_;
-                const float dd = d_ / s_;
+                double s_ = 0.0, d_ = 0.0;
                 for (int i = lane; i < N; i += 32) {
                     const float v = V[i];
                     if (v != 0.f) {
                         const float g = (blocked && i == goal_idx) ? 0.f : __ldg(gG + i);
-                        ACC[i] = fmaf(v * inv, g - dd, ACC[i]);
+                        s_ += double(v);
+                        d_ += double(g) * double(v);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    s_ += __shfl_xor_sync(kFull, s_, o);
+                    d_ += __shfl_xor_sync(kFull, d_, o);
+                }
+                const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
+                const double inv = (last ? double(Tb - t) : 1.0) / s_;
+                const double dd = d_ / s_;
+                for (int i = lane; i < N; i += 32) {
+                    const float v = V[i];
+                    if (v != 0.f) {
+                        const float g = (blocked && i == goal_idx) ? 0.f : __ldg(gG + i);
+                        ACC[i] += double(v) * inv * (double(g) - dd);
                     }
                 }
                 if (last) break;
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         if (kBwd) {
             const float coef = -omg / a.sqrt_w;
             float* gOut = a.grad_cost + int64_t(b) * N;
-            for (int i = lane; i < N; i += 32) gOut[i] = coef * ACC[i];
+            for (int i = lane; i < N; i += 32) gOut[i] = float(double(coef) * ACC[i]);
             __syncwarp();
         }
         if (!kBwd) {

@@ -47,7 +47,7 @@ while time.time() - t0 < budget:
             ts_bwd = torch.from_numpy(np.where(clamped, 0, Tbi).astype(np.int32)).cuda()
         gc = _native.backward(c, torch.from_numpy(start).cuda(), torch.from_numpy(goal).cuda(), o, torch.from_numpy(G).cuda(), Tb, ts_bwd, g_ratio)
         want = oracle.backward(cost, start, goal, obst, G, int(Tb.item()), g_ratio=g_ratio)
-        err = float(np.abs(gc.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-4 * np.abs(G).max() / (H * W)))
+        err = float(np.abs(gc.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-3 * np.abs(G).max() / np.sqrt(W)))
         if not (err < 1e-5):
             print("BWD MISMATCH", H, W, B, g_ratio, T, err); sys.exit(1)
     n += 1; cells += B
