@@ -48,7 +48,8 @@ while time.time() - t0 < budget:
         gc = _native.backward(c, torch.from_numpy(start).cuda(), torch.from_numpy(goal).cuda(), o, torch.from_numpy(G).cuda(), Tb, ts_bwd, g_ratio)
         want = oracle.backward(cost, start, goal, obst, G, int(Tb.item()), g_ratio=g_ratio)
         err = float(np.abs(gc.cpu().numpy() - want).max() / max(np.abs(want).max(), 1e-3 * np.abs(G).max() / np.sqrt(W)))
-        if not (err < 1e-5):
+        absdiff = float(np.abs(gc.cpu().numpy() - want).max())
+        if not (err < 1e-5 or absdiff < 1e-6 * float(np.abs(G).max())):   # near-zero gradients: compare absolutely
             print("BWD MISMATCH", H, W, B, g_ratio, T, err); sys.exit(1)
     n += 1; cells += B
 print(f"stress ok: {n} problems, {cells} maps in {time.time() - t0:.0f} s")
