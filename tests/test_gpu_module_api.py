@@ -184,3 +184,43 @@ def test_encoder_eval_fast_path_matches_module(arch, inp, depth, const, shape):
         na.encoder.model[0].weight.mul_(1.5)
         fast2 = na.encode(x, s, g)
     assert float((fast2 - fast).abs().max()) > 1e-4
+
+
+def test_graphed_planner_matches_eager():
+    """GraphedPlanner (CUDA-graph replay) returns the same, caller-owned outputs as the eager call."""
+    import os
+
+    from neural_astar import _native
+    from neural_astar.planner import NeuralAstar, VanillaAstar
+    from neural_astar.utils.inference import GraphedPlanner
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = Golden("mazes032_vanilla_test")
+    state = np.load(os.path.join(root, "tests", "golden", "mazes032_ckpt_planner_state.npz"))
+    na = NeuralAstar(encoder_arch="CNN")
+    na.load_state_dict({k: torch.from_numpy(state[k]) for k in state.files})
+    na = na.cuda().eval()
+    maps, start, goal = (torch.from_numpy(x).cuda() for x in (g.obst, g.start, g.goal))
+    with torch.no_grad():
+        want = na(maps, start, goal)
+    fast = GraphedPlanner(na, maps, start, goal)
+    assert fast.native_launches_per_replay == 1
+    # a different batch of the same shape through the captured graph
+    perm = torch.randperm(maps.shape[0], device="cuda")
+    with torch.no_grad():
+        want2 = na(maps[perm], start[perm], goal[perm])
+    got2 = fast(maps[perm], start[perm], goal[perm])
+    got = fast(maps, start, goal)
+    assert torch.equal(got.histories, want.histories) and torch.equal(got.paths, want.paths)
+    assert torch.equal(got2.histories, want2.histories) and torch.equal(got2.paths, want2.paths)   # got2 not overwritten
+    assert got.intermediate_results == [] and fast.replays == 2
+    # vanilla planner, host inputs straight into the static buffers
+    va = GraphedPlanner(VanillaAstar().cuda().eval(), maps, start, goal)
+    for dst, src in zip(va.static_inputs, (g.obst, g.start, g.goal)):
+        dst.copy_(torch.from_numpy(src).pin_memory(), non_blocking=True)
+    out = va.replay()
+    np.testing.assert_array_equal(out.histories.cpu().numpy() != 0, g.bits("hist_bits") != 0)
+    with pytest.raises(ValueError):
+        fast(maps[:5], start[:5], goal[:5])
+    with pytest.raises(ValueError):
+        GraphedPlanner(NeuralAstar().cuda().train(), maps, start, goal)
