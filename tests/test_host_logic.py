@@ -249,3 +249,77 @@ def test_two_rank_sharding_over_gloo():
         assert r[2] == 101 and r[3] == full_sum and r[4] == 2.0
     assert res[0][5] == float(torch.arange(4).sum())
     assert res[1][5] == float(torch.arange(51 * 4, 51 * 4 + 4).sum())
+
+
+# ---- host-side module logic exercised on CPU with the engine call replaced by the oracle ------------------
+class _FakeNative:
+    """Stands in for neural_astar._native in CPU tests: same call signatures, results from the SPEC oracle.
+    (Only the Python host logic around the engine is under test here; GPU tests cover the real engine.)"""
+
+    def __init__(self, oracle):
+        self.oracle = oracle
+        self.calls = []
+
+    def forward(self, cost, start, goal, obst, g_ratio, T, want_trace=False, no_early_exit=False):
+        self.calls.append((int(T), bool(want_trace), bool(no_early_exit)))
+        o = self.oracle.forward(cost.detach().numpy(), start.numpy(), goal.numpy(), obst.detach().numpy(),
+                                g_ratio=g_ratio, mode="spec", want_trace=True, T=T, no_early_exit=no_early_exit)
+        tr = torch.from_numpy(o.trace) if want_trace else None
+        return (torch.from_numpy(o.histories), torch.from_numpy(o.paths), torch.from_numpy(o.t_solve),
+                torch.from_numpy(o.n_steps), tr)
+
+    def batch_steps(self, t_solve, n_steps, T):
+        v = torch.where(t_solve >= 0, t_solve + 1, torch.full_like(t_solve, T))
+        return torch.clamp(v.max(), max=T).reshape(1).to(torch.int32)
+
+
+@pytest.fixture
+def fake_engine(oracle, monkeypatch):
+    from neural_astar.planner import differentiable_astar as da
+
+    fake = _FakeNative(oracle)
+    monkeypatch.setattr(da, "_native", fake)
+    return fake
+
+
+def test_intermediate_frames_host_logic(fake_engine):
+    """_materialise_frames: T_batch+1 frames, frame t = (closed set before step t, node selected at t), solved maps
+    repeat their goal, last frame = (histories, paths) — against the reference's own trace (golden)."""
+    from golden_util import Golden
+    from neural_astar.planner.differentiable_astar import DifferentiableAstar
+
+    g = Golden("mazes032_vanilla_gr07")
+    astar = DifferentiableAstar(g_ratio=g.g_ratio).eval()
+    t = [torch.from_numpy(x) for x in (g.cost, g.start, g.goal, g.obst)]
+    out = astar(*t, store_intermediate_results=True)
+    ref = g.z["trace"]
+    assert len(out.intermediate_results) == int(g.z["T_batch"]) + 1 == ref.shape[1] + 1
+    sel = torch.stack([f["paths"].reshape(g.B, -1).argmax(1) for f in out.intermediate_results[:-1]], 1).numpy()
+    np.testing.assert_array_equal(sel, ref)
+    closed = np.stack([f["histories"].reshape(g.B, -1).sum(1).numpy() for f in out.intermediate_results[:-1]], 1)
+    np.testing.assert_array_equal(closed, np.minimum(np.arange(ref.shape[1])[None, :], g.z["hist_sum"][:, None]))
+    assert torch.equal(out.intermediate_results[-1]["paths"], out.paths)
+    assert fake_engine.calls == [(32 * 32, True, False)]
+    assert astar(*t).intermediate_results == []
+
+
+@pytest.mark.parametrize("name", ["mazes032_lowg_gr00_cost10", "mazes032_lowg_gr04_cost10"])
+def test_batch_coupled_host_procedure(fake_engine, name):
+    """g_ratio < 0.5, B > 1: trace without early exit -> first step at which all maps select their goal -> rerun for
+    exactly that many steps.  Masks, T_batch and every frame equal the reference's (golden)."""
+    from golden_util import Golden
+    from neural_astar.planner.differentiable_astar import DifferentiableAstar
+
+    g = Golden(name)
+    astar = DifferentiableAstar(g_ratio=g.g_ratio).eval()
+    t = [torch.from_numpy(x) for x in (g.cost, g.start, g.goal, g.obst)]
+    out = astar(*t, store_intermediate_results=True)
+    Tb = int(g.z["T_batch"])
+    assert fake_engine.calls == [(1024, True, True), (Tb, True, True)]
+    np.testing.assert_array_equal(out.histories.numpy() != 0, g.bits("hist_bits") != 0)
+    np.testing.assert_array_equal(out.paths.numpy() != 0, g.bits("path_bits") != 0)
+    assert len(out.intermediate_results) == Tb + 1
+    # B == 1 or g_ratio >= 0.5 never take the coupled path
+    fake_engine.calls.clear()
+    astar(*[x[:1] for x in t])
+    assert fake_engine.calls == [(1024, False, False)]
