@@ -272,6 +272,12 @@ class _FakeNative:
         v = torch.where(t_solve >= 0, t_solve + 1, torch.full_like(t_solve, T))
         return torch.clamp(v.max(), max=T).reshape(1).to(torch.int32)
 
+    def backward(self, cost, start, goal, obst, grad_hist, T_batch, t_solve, g_ratio):
+        self.calls.append(("bwd", int(T_batch.item()), t_solve.clone()))
+        gc = self.oracle.backward(cost.detach().numpy(), start.numpy(), goal.numpy(), obst.detach().numpy(),
+                                  grad_hist.numpy(), int(T_batch.item()), g_ratio=g_ratio)
+        return torch.from_numpy(gc)
+
 
 @pytest.fixture
 def fake_engine(oracle, monkeypatch):
@@ -323,3 +329,46 @@ def test_batch_coupled_host_procedure(fake_engine, name):
     fake_engine.calls.clear()
     astar(*[x[:1] for x in t])
     assert fake_engine.calls == [(1024, False, False)]
+
+
+def test_autograd_wiring_on_cpu(fake_engine):
+    """_AstarSearch: histories carry grad, paths do not; backward gets the device-side T_batch and returns
+    dL/dcost with the cost tensor's shape (extra channels receive zeros) — L1 training loss vs the reference's
+    autograd gradient (golden)."""
+    from golden_util import Golden
+    from neural_astar.planner.differentiable_astar import DifferentiableAstar
+
+    g = Golden("mazes032_neural_test")
+    astar = DifferentiableAstar(g_ratio=0.5, Tmax=g.meta["train_Tmax"]).train()
+    cost2 = torch.from_numpy(np.concatenate([g.cost, np.full_like(g.cost, 3.0)], 1)).requires_grad_(True)  # [B,2,H,W]
+    start, goal, obst = (torch.from_numpy(x) for x in (g.start, g.goal, g.obst))
+    out = astar(cost2, start, goal, obst)
+    assert out.histories.requires_grad and not out.paths.requires_grad
+    opt = torch.from_numpy(g.bits("opt_bits").astype(np.float32))
+    torch.nn.L1Loss()(out.histories, opt).backward()
+    kind, Tb, _ = fake_engine.calls[-1]
+    assert kind == "bwd" and Tb == int(g.z["train_T_batch"]) and fake_engine.calls[0] == (256, False, False)
+    grad = cost2.grad.numpy()
+    assert grad.shape == cost2.shape and not grad[:, 1].any()
+    ref = g.plane("train_grad_cost")
+    assert np.abs(grad[:, :1] - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def test_coupled_backward_passes_goal_clamp_encoding(fake_engine):
+    """g_ratio < 0.5: the backward receives T_batch = the coupled step count and the 0 / T encoding of 'goal selected
+    at least twice' (include/nastar_b200.h, nastar_bwd_params.t_solve)."""
+    from golden_util import Golden
+    from neural_astar.planner.differentiable_astar import DifferentiableAstar
+
+    g = Golden("mazes032_lowg_gr00_cost10")
+    astar = DifferentiableAstar(g_ratio=g.g_ratio).eval()
+    cost = torch.from_numpy(g.cost).requires_grad_(True)
+    out = astar(cost, torch.from_numpy(g.start), torch.from_numpy(g.goal), torch.from_numpy(g.obst))
+    (out.histories * torch.from_numpy(g.plane("rand_G").astype(np.float32))).sum().backward()
+    kind, Tb, enc = fake_engine.calls[-1]
+    Tbatch = int(g.z["T_batch"])
+    assert kind == "bwd" and Tb == Tbatch
+    twice = (g.z["trace"] == g.z["goal_idx"][:, None]).sum(1) >= 2
+    np.testing.assert_array_equal(enc.numpy(), np.where(twice, 0, Tbatch))
+    ref = g.plane("rand_grad_cost")
+    assert np.abs(cost.grad.numpy() - ref).max() / np.abs(ref).max() < 1e-5
