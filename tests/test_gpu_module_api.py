@@ -224,3 +224,26 @@ def test_graphed_planner_matches_eager():
         fast(maps[:5], start[:5], goal[:5])
     with pytest.raises(ValueError):
         GraphedPlanner(NeuralAstar().cuda().train(), maps, start, goal)
+
+
+def test_warcraft_config_matches_reference_end_to_end():
+    """Config 4 shape end to end on the GPU: reference weights, 96x96 RGB -> 12x12 costs -> search with
+    learn_obstacles; the reference's CPU histories/paths are reproduced when fed its cost maps, and the cuDNN encoder's
+    cost maps agree with the reference's to TF32 accuracy."""
+    import os
+
+    from neural_astar.planner import NeuralAstar
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    z = np.load(os.path.join(root, "tests", "golden", "warcraft_encoder_ckpt.npz"))
+    na = NeuralAstar(encoder_input="rgb+", encoder_arch="CNNDownSize", encoder_depth=3, learn_obstacles=True, const=10.0)
+    na.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")})
+    na = na.cuda().eval()
+    x = torch.from_numpy(z["x"].astype(np.float32)).cuda()
+    s, g = torch.from_numpy(z["start"]).cuda(), torch.from_numpy(z["goal"]).cuda()
+    with torch.no_grad():
+        cost = na.encode(x, s, g)
+    assert float((cost.cpu() - torch.from_numpy(z["cost"])).abs().max()) < 3e-2          # const=10, TF32 convs
+    out = na.perform_astar(torch.from_numpy(z["cost"]).cuda(), s, g, torch.ones_like(s))
+    np.testing.assert_array_equal(out.histories.cpu().numpy() != 0, z["hist"] != 0)
+    np.testing.assert_array_equal(out.paths.cpu().numpy() != 0, z["paths"] != 0)

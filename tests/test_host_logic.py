@@ -372,3 +372,19 @@ def test_coupled_backward_passes_goal_clamp_encoding(fake_engine):
     np.testing.assert_array_equal(enc.numpy(), np.where(twice, 0, Tbatch))
     ref = g.plane("rand_grad_cost")
     assert np.abs(cost.grad.numpy() - ref).max() / np.abs(ref).max() < 1e-5
+
+
+def test_warcraft_encoder_handoff_matches_reference():
+    """Config-4 hand-off on CPU: CNNDownSize(depth 3, const 10) with the reference's weights reproduces the reference's
+    cost maps on a 96x96 RGB batch whose start/goal marks are nearest-upsampled from 12x12 (planner/astar.py:172-177)."""
+    from neural_astar.planner import NeuralAstar
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "warcraft_encoder_ckpt.npz"))
+    na = NeuralAstar(encoder_input="rgb+", encoder_arch="CNNDownSize", encoder_depth=3, learn_obstacles=True, const=10.0)
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")}
+    assert str(na.load_state_dict(sd)) == "<All keys matched successfully>"
+    na.eval()
+    x = torch.from_numpy(z["x"].astype(np.float32))
+    with torch.no_grad():
+        cost = na.encode(x, torch.from_numpy(z["start"]), torch.from_numpy(z["goal"]))
+    np.testing.assert_allclose(cost.numpy(), z["cost"], rtol=1e-5, atol=1e-5)
