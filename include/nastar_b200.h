@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NASTAR_B200_ABI_VERSION 1
+#define NASTAR_B200_ABI_VERSION 2
 
 /* status codes (the reference only has Python asserts, differentiable_astar.py:147,172-175) */
 enum {
@@ -46,6 +46,22 @@ enum {
                                       loop does until the slowest map is solved (differentiable_astar.py:251-252).
                                       Per-map early exit is exact for g_ratio >= 0.5; the host
                                       side uses this flag to reproduce the batch coupling for g_ratio < 0.5 */
+#define NASTAR_FWD_PAIR 2          /* validation pair in ONE launch (utils/training.py:63-87 runs the learned-cost
+                                      search and VanillaAstar on the same batch): maps 0..B-1 are searched on
+                                      `cost` (any cost_kind), maps B..2B-1 are the same problems searched with
+                                      cost = obst (astar.py:93-94).  Every output array then holds 2B entries.
+                                      Engine-1 shapes (H,W <= 32) run both halves in one kernel launch; other
+                                      shapes issue the two halves back to back inside this call */
+
+/* nastar_fwd_params.cost_kind: what `cost` points to (encoder -> search hand-off) */
+#define NASTAR_COST_PLANE 0  /* finished cost maps, fp32 [B][H*W] (differentiable_astar.py:150-157) */
+#define NASTAR_COST_LOGIT 1  /* the encoder's raw 1-channel output x, fp32 [B][H*W]; the kernel prologue applies
+                                encoder.py:32-34: cost = sigmoid(x) * cost_scale */
+#define NASTAR_COST_TAPS  2  /* per-pixel partial products of the encoder's last 3x3 conv (one output channel),
+                                fp32 [B][H*W][9] (tap k = ky*3+kx innermost): the prologue gathers
+                                x[y][x] = cost_bias + sum_k taps[y+ky-1][x+kx-1][k] (zero padding), then
+                                cost = sigmoid(x) * cost_scale.  `cost_stride` is in elements of this layout
+                                (9*H*W for a dense batch).  Engine-1 shapes only */
 
 typedef struct nastar_fwd_params {
     /* inputs — differentiable_astar.py:150-157 (cost_maps, start_maps, goal_maps, obstacles_maps) */
@@ -62,6 +78,11 @@ typedef struct nastar_fwd_params {
     int32_t T;
     /* NASTAR_FWD_* flags */
     int32_t flags;
+    /* NASTAR_COST_*; cost_scale = the encoder's `const` (encoder.py:25-28,34), cost_bias = folded bias of the
+       last conv (NASTAR_COST_TAPS only).  Zero-initialised params mean a plain cost plane */
+    int32_t cost_kind;
+    float   cost_scale;
+    float   cost_bias;
     /* outputs */
     float   *histories;  /* [B][H*W] fp32 in {0,1}   — AstarOutput.histories, :265 */
     int64_t *paths;      /* [B][H*W] int64 in {0,1}  — AstarOutput.paths (backtrack, :96-125) */
@@ -69,6 +90,9 @@ typedef struct nastar_fwd_params {
     int32_t *n_steps;    /* [B] number of selection steps executed for the map; nullable */
     int32_t *trace;      /* [B][T] selected flat index per step (-1 beyond n_steps); nullable.
                             Feeds store_intermediate_results (:210-216) */
+    int32_t *n_closed;   /* [B] number of closed cells = histories.sum() per map; nullable.  With path_len it
+                            replaces the host-side sums of the validation metrics (utils/training.py:71-85) */
+    int32_t *path_len;   /* [B] number of cells on the path = paths.sum() per map; nullable */
     /* scratch for maps whose state does not fit in shared memory; see
        nastar_b200_forward_workspace_bytes().  nullable when that returns 0 */
     void    *workspace;
@@ -106,8 +130,10 @@ typedef struct nastar_bwd_params {
 /* ABI version of the loaded library (== NASTAR_B200_ABI_VERSION at build time). */
 int nastar_b200_abi_version(void);
 
-/* Bytes of device scratch nastar_b200_forward needs for this shape (0 for maps that fit
- * in shared memory, i.e. every BASELINE.json config up to 64x128). */
+/* Bytes of device scratch nastar_b200_forward needs for this shape: 0 for H,W <= 64 (every 32x32 / 12x12 / 64x64
+ * config); larger maps need the work queue + per-map flags of the binary-cost engine and, beyond 128x128, the
+ * per-CTA state slots of the generic engine.  Passing less than this but at least the generic engine's own need
+ * still works (the binary-cost fast path is then skipped). */
 size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W);
 size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W);
 
@@ -125,8 +151,28 @@ int nastar_b200_batch_steps(const int32_t *t_solve, const int32_t *n_steps, int3
 
 /* Which forward engine a shape dispatches to: 1 = warp-resident (H,W <= 32), 4 = warp-resident 64-wide
  * (H,W <= 64), 2 = generic warp engine with shared-memory state, 3 = generic with global-memory state,
- * 0 = unsupported.  (The backward of engine-4 shapes runs on the generic engine.) */
+ * 0 = unsupported.  (The backward of engine-4 shapes runs on the generic engine.)  Engine-2/3 shapes whose cost
+ * plane IS the obstacle plane (same pointer and stride: VanillaAstar, astar.py:93-94) are first offered to
+ * engine 5, the CTA-per-map binary-cost engine (csrc/nastar_bin16.cuh); maps it cannot take (a cost value
+ * outside {0,1}) are re-run by engine 2/3 inside the same call. */
 int nastar_b200_engine_for(int32_t H, int32_t W);
+
+/* 1 if engine 5 (binary-cost, whole map in one CTA's shared memory) can hold this shape. */
+int nastar_b200_bin16_supported(int32_t H, int32_t W);
+
+/* Encoder input assembly, replaces NeuralAstar.encode's glue (astar.py:172-177): out is the channels-last
+ * (NHWC) tensor [B][Hm][Wm][C+1] with channels 0..C-1 = map_designs[b][c] (fp32 NCHW [B][C][Hm][Wm], contiguous)
+ * and channel C = (start + goal) nearest-upsampled from [H][W] to [Hm][Wm] (F.interpolate mode="nearest";
+ * identity when the sizes agree).  start/goal are [B][H*W] planes with element strides. */
+int nastar_b200_pack_inputs(const float *map_designs, int32_t C, int32_t Hm, int32_t Wm,
+                            const float *start, int64_t start_stride, const float *goal, int64_t goal_stride,
+                            int32_t B, int32_t H, int32_t W, float *out, void *stream);
+
+/* cost = sigmoid(bias + 9-tap gather of `taps`) * scale for every cell, written as a dense [B][H*W] plane — the
+ * same arithmetic, in the same order, as nastar_b200_forward's NASTAR_COST_TAPS prologue (so `encode()` and the
+ * fused forward agree bit for bit).  taps: fp32 [B][H*W][9]. */
+int nastar_b200_cost_from_taps(const float *taps, int32_t B, int32_t H, int32_t W, float bias, float scale,
+                               float *cost, void *stream);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t nastar_b200_launch_count(void);

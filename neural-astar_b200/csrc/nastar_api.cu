@@ -4,8 +4,12 @@
 #include <atomic>
 #include <cstdio>
 
+#include <cstdlib>
+
 #include "../../include/nastar_b200.h"
+#include "nastar_bin16.cuh"
 #include "nastar_generic.cuh"
+#include "nastar_glue.cuh"
 #include "nastar_warp32.cuh"
 #include "nastar_warp64.cuh"
 
@@ -76,6 +80,27 @@ int generic_slots(int B) {
     return B < cap ? B : cap;
 }
 
+// ---- engine 5 (nastar_bin16.cuh): binary-cost maps, one CTA per map --------------------------------------
+// NASTAR_B200_BIN16=0 in the environment disables it (A/B measurements against engines 2/3)
+bool bin16_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("NASTAR_B200_BIN16");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+bool bin16_shape_ok(int32_t H, int32_t W) {
+    if (H <= 0 || W <= 0 || (H <= 64 && W <= 64)) return false;   // engines 1 / 4 keep their shapes
+    if (generic_engine_for(H, W) == 0) return false;
+    const nastar::Bin16Layout L(H, W);
+    return L.supported() && L.smem_bytes() <= kMaxDynSmem;
+}
+
+// head of the workspace when engine 5 may run: [0,256) work-queue counter, then B redo flags (256-B granules)
+size_t bin16_aux_bytes(int32_t B) { return 256 + ((size_t(B) * 4 + 255) & ~size_t(255)); }
+
 inline int cuda_fail(cudaError_t e) {
     g_last_err = e;
     return NASTAR_ECUDA;
@@ -116,9 +141,15 @@ int nastar_b200_engine_for(int32_t H, int32_t W) {
     return generic_engine_for(H, W);
 }
 
+int nastar_b200_bin16_supported(int32_t H, int32_t W) { return bin16_shape_ok(H, W) ? 1 : 0; }
+
 size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
-    if (B <= 0 || nastar_b200_engine_for(H, W) != 3) return 0;
-    return size_t(generic_slots(B)) * nastar::GenericLayout(H, W).slot_bytes();
+    if (B <= 0) return 0;
+    const int engine = nastar_b200_engine_for(H, W);
+    if (engine != 2 && engine != 3) return 0;
+    size_t n = (engine == 3) ? size_t(generic_slots(B)) * nastar::GenericLayout(H, W).slot_bytes() : 0;
+    if (bin16_enabled() && bin16_shape_ok(H, W)) n += bin16_aux_bytes(B);
+    return n;
 }
 
 size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
@@ -131,11 +162,33 @@ size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
 int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
     if (!p || !p->cost || !p->start || !p->goal || !p->obst || !p->histories || !p->paths) return NASTAR_EINVAL;
     if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->T < 1) return NASTAR_EINVAL;
+    if (p->cost_kind < NASTAR_COST_PLANE || p->cost_kind > NASTAR_COST_TAPS) return NASTAR_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int engine = nastar_b200_engine_for(p->H, p->W);
     if (engine == 0) return NASTAR_EUNSUPPORTED;
+    if (p->cost_kind != NASTAR_COST_PLANE && engine != 1) return NASTAR_EUNSUPPORTED;   // fused hand-off: H,W <= 32
+    const bool pair = (p->flags & NASTAR_FWD_PAIR) != 0;
+    if (pair && engine != 1) {
+        // two halves back to back: the learned-cost search, then the same problems with cost = obstacles
+        const int64_t N = int64_t(p->H) * p->W;
+        nastar_fwd_params h = *p;
+        h.flags &= ~NASTAR_FWD_PAIR;
+        int st = nastar_b200_forward(&h, stream_v);
+        if (st != NASTAR_OK) return st;
+        h.cost = p->obst;
+        h.cost_stride = p->obst_stride;
+        h.histories = p->histories + int64_t(p->B) * N;
+        h.paths = p->paths + int64_t(p->B) * N;
+        if (p->t_solve) h.t_solve = p->t_solve + p->B;
+        if (p->n_steps) h.n_steps = p->n_steps + p->B;
+        if (p->trace) h.trace = p->trace + int64_t(p->B) * p->T;
+        if (p->n_closed) h.n_closed = p->n_closed + p->B;
+        if (p->path_len) h.path_len = p->path_len + p->B;
+        return nastar_b200_forward(&h, stream_v);
+    }
+    const int nmaps = pair ? 2 * p->B : p->B;   // output slots (= CTAs of the warp32 engine)
     if (p->trace) {
-        cudaError_t e = cudaMemsetAsync(p->trace, 0xFF, size_t(p->B) * size_t(p->T) * sizeof(int32_t), stream);
+        cudaError_t e = cudaMemsetAsync(p->trace, 0xFF, size_t(nmaps) * size_t(p->T) * sizeof(int32_t), stream);
         if (e != cudaSuccess) return cuda_fail(e);
     }
     if (engine == 1) {
@@ -145,11 +198,11 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         a.f = *p;
         const bool noexit = (p->flags & NASTAR_FWD_NO_EARLY_EXIT) != 0;
         if (p->trace) {
-            if (noexit) nastar::astar_warp32_kernel<true, false, true><<<p->B, 32, 0, stream>>>(a);
-            else nastar::astar_warp32_kernel<true, false, false><<<p->B, 32, 0, stream>>>(a);
+            if (noexit) nastar::astar_warp32_kernel<true, false, true><<<nmaps, 32, 0, stream>>>(a);
+            else nastar::astar_warp32_kernel<true, false, false><<<nmaps, 32, 0, stream>>>(a);
         } else {
-            if (noexit) nastar::astar_warp32_kernel<false, false, true><<<p->B, 32, 0, stream>>>(a);
-            else nastar::astar_warp32_kernel<false, false, false><<<p->B, 32, 0, stream>>>(a);
+            if (noexit) nastar::astar_warp32_kernel<false, false, true><<<nmaps, 32, 0, stream>>>(a);
+            else nastar::astar_warp32_kernel<false, false, false><<<nmaps, 32, 0, stream>>>(a);
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (engine == 4) {
@@ -173,12 +226,41 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         const bool global = (engine == 3);
         const size_t smem = L.smem_common() + (global ? 0 : L.smem_planes());
         int grid = p->B;
+        const size_t slots_bytes = global ? size_t(generic_slots(p->B)) * L.slot_bytes() : 0;
         if (global) {
             grid = generic_slots(p->B);
-            if (!p->workspace || p->workspace_bytes < size_t(grid) * L.slot_bytes()) return NASTAR_EWORKSPACE;
+            if (!p->workspace || p->workspace_bytes < slots_bytes) return NASTAR_EWORKSPACE;
         }
         nastar::GenArgs ga{};
         ga.f = *p;
+        // engine 5 first when the cost plane IS the binary obstacle plane (VanillaAstar / Config 5): whole map on
+        // chip, one CTA per SM pulling maps from a queue; maps it flags are re-run below by the generic engine
+        const bool aliased = (p->obst == p->cost) && (p->obst_stride == p->cost_stride);
+        const size_t aux = bin16_aux_bytes(p->B);
+        if (bin16_enabled() && aliased && !p->trace && p->flags == 0 && bin16_shape_ok(p->H, p->W) && p->workspace &&
+            p->workspace_bytes >= aux + slots_bytes) {
+            unsigned char* ws = static_cast<unsigned char*>(p->workspace);
+            nastar::Bin16Args ba{};
+            ba.f = *p;
+            ba.queue = reinterpret_cast<int32_t*>(ws);
+            ba.redo = reinterpret_cast<int32_t*>(ws + 256);
+            cudaError_t e = cudaMemsetAsync(ba.queue, 0, 256, stream);
+            if (e != cudaSuccess) return cuda_fail(e);
+            const size_t bsmem = nastar::Bin16Layout(p->H, p->W).smem_bytes();
+            e = cudaFuncSetAttribute(nastar::astar_bin16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bsmem));
+            if (e != cudaSuccess) return cuda_fail(e);
+            // resident CTAs per SM by shared memory (1 at 256x256, several for smaller maps)
+            int per_sm = int(kMaxDynSmem / (bsmem + 1024));
+            per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+            const int bgrid = p->B < num_sms() * per_sm ? p->B : num_sms() * per_sm;
+            nastar::astar_bin16_kernel<<<bgrid, nastar::kBin16Threads, bsmem, stream>>>(ba);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            ga.redo = ba.redo;
+            ga.f.workspace = ws + aux;
+            ga.f.workspace_bytes = p->workspace_bytes - aux;
+        }
         auto launch = [&](auto kernel) -> cudaError_t {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if (e != cudaSuccess) return e;
@@ -279,6 +361,39 @@ int nastar_b200_batch_steps(const int32_t* t_solve, const int32_t* n_steps, int3
     if (!t_solve || !T_batch || B <= 0 || T < 1) return NASTAR_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     batch_steps_kernel<<<1, 256, 0, stream>>>(t_solve, n_steps, B, T, T_batch);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
+}
+
+int nastar_b200_pack_inputs(const float* map_designs, int32_t C, int32_t Hm, int32_t Wm, const float* start,
+                            int64_t start_stride, const float* goal, int64_t goal_stride, int32_t B, int32_t H,
+                            int32_t W, float* out, void* stream_v) {
+    if (!map_designs || !start || !goal || !out || C <= 0 || Hm <= 0 || Wm <= 0 || B <= 0 || H <= 0 || W <= 0)
+        return NASTAR_EINVAL;
+    if ((C == 1 && (reinterpret_cast<uintptr_t>(out) & 7)) || (C == 3 && (reinterpret_cast<uintptr_t>(out) & 15)))
+        return NASTAR_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int64_t npix = int64_t(B) * Hm * Wm;
+    const int64_t want = (npix + 255) / 256;
+    const int grid = int(want < int64_t(num_sms()) * 16 ? want : int64_t(num_sms()) * 16);
+    nastar::pack_inputs_kernel<<<grid, 256, 0, stream>>>(map_designs, C, Hm, Wm, start, start_stride, goal, goal_stride,
+                                                         B, H, W, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
+}
+
+int nastar_b200_cost_from_taps(const float* taps, int32_t B, int32_t H, int32_t W, float bias, float scale,
+                               float* cost, void* stream_v) {
+    if (!taps || !cost || B <= 0 || H <= 0 || W <= 0) return NASTAR_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const int64_t total = int64_t(B) * H * W;
+    const int64_t want = (total + 255) / 256;
+    const int grid = int(want < int64_t(num_sms()) * 16 ? want : int64_t(num_sms()) * 16);
+    nastar::cost_from_taps_kernel<<<grid, 256, 0, stream>>>(taps, B, H, W, bias, scale, cost);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);

@@ -32,6 +32,39 @@ __device__ __forceinline__ float heuristic(int y, int x, int gy, int gx) {
     return __fadd_rn(cheb, __fmul_rn(0.001f, euc));
 }
 
+// encoder.py:32-34, cost = sigmoid(x) * const, with the operation sequence of ATen's CUDA sigmoid
+// (1 / (1 + exp(-x)), full-precision expf and IEEE division) followed by a separately rounded multiply.
+__device__ __forceinline__ float sigmoid_scaled(float x, float scale) {
+    return __fmul_rn(__fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))), scale);
+}
+
+// NASTAR_COST_TAPS: logit(y,x) = bias + sum_k taps[y+ky-1][x+kx-1][k], k = ky*3+kx ascending, zero padding —
+// the 9->1 gather that finishes the encoder's single-output-channel 3x3 convolution (planner/encoder.py
+// `_conv3x3_single_output`).  taps is one map's [H*W][9] block.
+__device__ __forceinline__ float cost_from_taps(const float* __restrict__ taps, int y, int x, int H, int W,
+                                                float bias, float scale) {
+    float acc = bias;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (unsigned(yy) < unsigned(H) && unsigned(xx) < unsigned(W))
+                acc = __fadd_rn(acc, __ldg(taps + (int64_t(yy) * W + xx) * 9 + (ky * 3 + kx)));
+        }
+    }
+    return sigmoid_scaled(acc, scale);
+}
+
+// one cost value under nastar_fwd_params.cost_kind (include/nastar_b200.h NASTAR_COST_*)
+__device__ __forceinline__ float cost_value(int kind, const float* __restrict__ src, int y, int x, int H, int W,
+                                            float bias, float scale) {
+    if (kind == 0) return __ldg(src + y * W + x);
+    if (kind == 1) return sigmoid_scaled(__ldg(src + y * W + x), scale);
+    return cost_from_taps(src, y, x, H, W, bias, scale);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -47,6 +47,9 @@ struct GenArgs {
     const float* grad_hist;
     int64_t grad_stride;
     float* grad_cost;
+    // forward only, nullable: per-map flags written by the bin16 engine (nastar_bin16.cuh); when given, only
+    // maps with redo[b] != 0 are processed here (the others were already finished on-chip)
+    const int32_t* redo;
 };
 
 __device__ __forceinline__ float gen_warp_sum(float v) {
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
     }
 
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        if (!kBwd && a.redo != nullptr && a.redo[b] == 0) continue;
         const float* gCost = p.cost + int64_t(b) * p.cost_stride;
         const float* gStart = p.start + int64_t(b) * p.start_stride;
         const float* gGoal = p.goal + int64_t(b) * p.goal_stride;
@@ -417,9 +421,17 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
                 }
             }
         }
+        int n_closed = 0, n_path = 0;
+        if (p.n_closed || p.path_len) {
+            for (int i = lane; i < L.nbits; i += 32) { n_closed += __popc(sClosed[i]); n_path += __popc(sPath[i]); }
+            n_closed = __reduce_add_sync(kFull, n_closed);
+            n_path = __reduce_add_sync(kFull, n_path);
+        }
         if (lane == 0) {
             if (p.t_solve) p.t_solve[b] = t_solve;
             if (p.n_steps) p.n_steps[b] = steps;
+            if (p.n_closed) p.n_closed[b] = n_closed;
+            if (p.path_len) p.path_len[b] = n_path;
         }
         }  // !kBwd
         __syncwarp();

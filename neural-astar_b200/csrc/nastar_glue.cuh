@@ -1,0 +1,58 @@
+// nastar_glue.cuh — the two small kernels either side of the encoder CNN.
+//
+// The encoder itself stays PyTorch/cuDNN (north star); what is replaced here is the element-wise glue of
+// NeuralAstar.encode (/root/reference/src/neural_astar/planner/astar.py:172-177: start+goal add, nearest
+// upsample, channel concat, plus the NCHW->NHWC conversion cuDNN's tensor-core convs want) and of
+// EncoderBase.forward (/root/reference/src/neural_astar/planner/encoder.py:32-34: sigmoid * const) —
+// seven ATen launches per forward in round 1, now one kernel in front of the convs and the search
+// kernel's own prologue behind them.
+#pragma once
+#include "../../include/nastar_b200.h"
+#include "nastar_common.cuh"
+
+namespace nastar {
+
+// out[b][ym][xm][0..C-1] = map_designs[b][c][ym][xm];  out[b][ym][xm][C] = (start+goal)[b][ys][xs] with the
+// source index of F.interpolate(mode="nearest"): min(floor(dst * in/out), in-1), scale evaluated in fp32.
+__global__ void __launch_bounds__(256) pack_inputs_kernel(const float* __restrict__ maps, int C, int Hm, int Wm,
+                                                          const float* __restrict__ start, int64_t start_stride,
+                                                          const float* __restrict__ goal, int64_t goal_stride,
+                                                          int B, int H, int W, float* __restrict__ out) {
+    const int64_t npix = int64_t(B) * Hm * Wm;
+    const float sh = float(H) / float(Hm), sw = float(W) / float(Wm);
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < npix; i += int64_t(gridDim.x) * blockDim.x) {
+        const int xm = int(i % Wm);
+        const int ym = int((i / Wm) % Hm);
+        const int b = int(i / (int64_t(Wm) * Hm));
+        int ys = ym, xs = xm;
+        if (H != Hm) ys = min(int(floorf(float(ym) * sh)), H - 1);
+        if (W != Wm) xs = min(int(floorf(float(xm) * sw)), W - 1);
+        const float mark = __fadd_rn(__ldg(start + int64_t(b) * start_stride + ys * W + xs),
+                                     __ldg(goal + int64_t(b) * goal_stride + ys * W + xs));
+        float* o = out + i * (C + 1);
+        const float* m = maps + (int64_t(b) * C * Hm + ym) * Wm + xm;
+        if (C == 1) {
+            *reinterpret_cast<float2*>(o) = make_float2(__ldg(m), mark);
+        } else if (C == 3) {
+            *reinterpret_cast<float4*>(o) = make_float4(__ldg(m), __ldg(m + int64_t(Hm) * Wm), __ldg(m + 2 * int64_t(Hm) * Wm), mark);
+        } else {
+            for (int c = 0; c < C; ++c) o[c] = __ldg(m + c * int64_t(Hm) * Wm);
+            o[C] = mark;
+        }
+    }
+}
+
+// dense cost plane from the 9-tap partial products: same device function as the search prologue
+__global__ void __launch_bounds__(256) cost_from_taps_kernel(const float* __restrict__ taps, int B, int H, int W,
+                                                             float bias, float scale, float* __restrict__ cost) {
+    const int N = H * W;
+    const int64_t total = int64_t(B) * N;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int b = int(i / N);
+        const int rc = int(i - int64_t(b) * N);
+        const int y = rc / W, x = rc - y * W;
+        cost[i] = cost_from_taps(taps + int64_t(b) * N * 9, y, x, H, W, bias, scale);
+    }
+}
+
+}  // namespace nastar

@@ -75,19 +75,24 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     const nastar_fwd_params& p = a.f;
     float2* const sGH = S.ghbuf + 2;
     const int lane = threadIdx.x;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x;                    // output slot
     const int H = p.H, W = p.W, N = H * W;
+    // NASTAR_FWD_PAIR: CTAs B..2B-1 search the same problems with cost = obstacles (VanillaAstar, astar.py:93-94)
+    const bool vanilla_half = !kBwd && (p.flags & NASTAR_FWD_PAIR) && (b >= p.B);
+    const int bi = vanilla_half ? (b - p.B) : b;  // input map
 
-    const float* gCost = p.cost + int64_t(b) * p.cost_stride;
-    const float* gStart = p.start + int64_t(b) * p.start_stride;
-    const float* gGoal = p.goal + int64_t(b) * p.goal_stride;
-    const float* gObst = p.obst + int64_t(b) * p.obst_stride;
-    const bool obst_is_cost = (gObst == gCost);
+    const float* gStart = p.start + int64_t(bi) * p.start_stride;
+    const float* gGoal = p.goal + int64_t(bi) * p.goal_stride;
+    const float* gObst = p.obst + int64_t(bi) * p.obst_stride;
+    const float* gCost = vanilla_half ? gObst : (p.cost + int64_t(bi) * p.cost_stride);
+    const int cost_kind = (kBwd || vanilla_half) ? NASTAR_COST_PLANE : p.cost_kind;
+    const bool cost_plane = (cost_kind == NASTAR_COST_PLANE);
+    const bool obst_is_cost = cost_plane && (gObst == gCost);
 
     // ---------------- prologue: stage planes, build row masks ------------------------------
     uint32_t pass = 0u;
     int start_rc = -1, goal_rc = -1;
-    const bool tma = (W == 32) && aligned16(gCost) && aligned16(gStart) && aligned16(gGoal) && aligned16(gObst);
+    const bool tma = (W == 32) && (!cost_plane || aligned16(gCost)) && aligned16(gStart) && aligned16(gGoal) && aligned16(gObst);
     if (tma) {
         // flat layout == padded layout: bulk-copy whole planes (start/goal/obstacles are parked in the
         // f and {g,h} planes, which are not live yet)
@@ -99,13 +104,20 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
             mbar_init(bar, 1);
             fence_mbar_init();
             const uint32_t bytes = uint32_t(N) * 4u;
-            mbar_expect_tx(bar, bytes * (obst_is_cost ? 3u : 4u));
-            tma_load_1d(S.cost, gCost, bytes, bar);
+            mbar_expect_tx(bar, bytes * ((obst_is_cost ? 3u : 4u) - (cost_plane ? 0u : 1u)));
+            if (cost_plane) tma_load_1d(S.cost, gCost, bytes, bar);
             tma_load_1d(tStart, gStart, bytes, bar);
             tma_load_1d(tGoal, gGoal, bytes, bar);
             if (!obst_is_cost) tma_load_1d(tObst, gObst, bytes, bar);
         }
         __syncwarp();
+        if (!cost_plane) {
+            // fused encoder hand-off: the cost plane is produced here from the encoder's raw
+            // output while the TMA copies of the other planes are in flight
+#pragma unroll 4
+            for (int y = 0; y < H; ++y)
+                S.cost[(y << 5) + lane] = cost_value(cost_kind, gCost, y, lane, H, W, p.cost_bias, p.cost_scale);
+        }
         mbar_wait(bar, 0);
         const float* sObst = obst_is_cost ? S.cost : tObst;
 #pragma unroll 4
@@ -129,7 +141,7 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
             for (int u = 0; u < kRows; ++u) {
                 const bool ok = in && (y0 + u < H);
                 const int i = (y0 + u) * W + lane;
-                vc[u] = ok ? __ldg(gCost + i) : 0.f;
+                vc[u] = ok ? cost_value(cost_kind, gCost, y0 + u, lane, H, W, p.cost_bias, p.cost_scale) : 0.f;
                 vo[u] = obst_is_cost ? vc[u] : (ok ? __ldg(gObst + i) : 0.f);
                 vs[u] = ok ? __ldg(gStart + i) : 0.f;
                 vg[u] = ok ? __ldg(gGoal + i) : 0.f;
@@ -400,9 +412,14 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
             }
         }
     }
+    // per-map counts for the validation metrics (utils/training.py:71-85): histories.sum(), paths.sum()
+    const int n_closed = __reduce_add_sync(kFull, __popc(closed));
+    const int n_path = __reduce_add_sync(kFull, __popc(path));
     if (lane == 0) {
         if (p.t_solve) p.t_solve[b] = t_solve;
         if (p.n_steps) p.n_steps[b] = steps;
+        if (p.n_closed) p.n_closed[b] = n_closed;
+        if (p.path_len) p.path_len[b] = n_path;
     }
 }
 

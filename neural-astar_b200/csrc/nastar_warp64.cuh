@@ -298,9 +298,13 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const nastar_fwd_param
             }
         }
     }
+    const int n_closed = __reduce_add_sync(kFull, __popcll(closed[0]) + __popcll(closed[1]));
+    const int n_path = __reduce_add_sync(kFull, __popcll(path0) + __popcll(path1));
     if (lane == 0) {
         if (p.t_solve) p.t_solve[b] = t_solve;
         if (p.n_steps) p.n_steps[b] = steps;
+        if (p.n_closed) p.n_closed[b] = n_closed;
+        if (p.path_len) p.path_len[b] = n_path;
     }
 }
 

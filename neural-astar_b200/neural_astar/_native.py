@@ -17,7 +17,7 @@ import torch
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # neural-astar_b200/
 LIB_PATH = os.environ.get("NASTAR_B200_LIB", os.path.join(_PKG_ROOT, "lib", "libnastar_b200.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NASTAR_OK = 0
 TS_CAPPED = -1
 TS_EXHAUSTED = -2
@@ -36,8 +36,10 @@ class FwdParams(ctypes.Structure):
         ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
         ("g_ratio", ctypes.c_float), ("one_minus_g_ratio", ctypes.c_float),
         ("T", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("cost_kind", ctypes.c_int32), ("cost_scale", ctypes.c_float), ("cost_bias", ctypes.c_float),
         ("histories", ctypes.c_void_p), ("paths", ctypes.c_void_p),
         ("t_solve", ctypes.c_void_p), ("n_steps", ctypes.c_void_p), ("trace", ctypes.c_void_p),
+        ("n_closed", ctypes.c_void_p), ("path_len", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
     ]
 
@@ -67,6 +69,9 @@ EXPORTS = (
     "nastar_b200_backward",
     "nastar_b200_batch_steps",
     "nastar_b200_engine_for",
+    "nastar_b200_bin16_supported",
+    "nastar_b200_pack_inputs",
+    "nastar_b200_cost_from_taps",
     "nastar_b200_launch_count",
     "nastar_b200_status_string",
     "nastar_b200_last_cuda_error",
@@ -106,6 +111,16 @@ def lib():
     L.nastar_b200_batch_steps.restype = ctypes.c_int
     L.nastar_b200_engine_for.argtypes = [ctypes.c_int32, ctypes.c_int32]
     L.nastar_b200_engine_for.restype = ctypes.c_int
+    L.nastar_b200_bin16_supported.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    L.nastar_b200_bin16_supported.restype = ctypes.c_int
+    L.nastar_b200_pack_inputs.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                          ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                          ctypes.c_void_p]
+    L.nastar_b200_pack_inputs.restype = ctypes.c_int
+    L.nastar_b200_cost_from_taps.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                             ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+    L.nastar_b200_cost_from_taps.restype = ctypes.c_int
     L.nastar_b200_launch_count.restype = ctypes.c_uint64
     L.nastar_b200_status_string.argtypes = [ctypes.c_int]
     L.nastar_b200_status_string.restype = ctypes.c_char_p
@@ -146,14 +161,26 @@ def launch_count() -> int:
 
 
 FWD_NO_EARLY_EXIT = 1
+FWD_PAIR = 2
+COST_PLANE, COST_LOGIT, COST_TAPS = 0, 1, 2
+
+
+class SearchCounts(tuple):
+    """(n_closed [B'] i32, path_len [B'] i32): histories.sum() / paths.sum() per map, written by the kernel."""
 
 
 def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: torch.Tensor,
-            g_ratio: float, T: int, want_trace: bool = False, no_early_exit: bool = False):
+            g_ratio: float, T: int, want_trace: bool = False, no_early_exit: bool = False, *,
+            pair: bool = False, cost_kind: int = COST_PLANE, cost_scale: float = 1.0, cost_bias: float = 0.0,
+            want_counts: bool = False):
     """Run the search for a batch of [B,C,H,W] fp32 CUDA planes (channel 0 is used).
 
-    Returns (histories [B,1,H,W] f32, paths [B,1,H,W] i64, t_solve [B] i32, n_steps [B] i32,
-    trace [B,T] i32 or None), all on the inputs' device, asynchronously on the current stream.
+    Returns (histories [B',1,H,W] f32, paths [B',1,H,W] i64, t_solve [B'] i32, n_steps [B'] i32,
+    trace [B',T] i32 or None), all on the inputs' device, asynchronously on the current stream; with
+    `want_counts` a sixth element (n_closed [B'], path_len [B']) is appended.  B' = 2B with `pair`
+    (NASTAR_FWD_PAIR: second half = the same problems with cost = obstacles), else B.
+    `cost_kind` = COST_LOGIT / COST_TAPS: `cost` holds the encoder's raw output [B,1,H,W] / the 9-tap partial
+    products [B,H,W,9] and the kernel prologue finishes encoder.py:32-34 itself (H, W <= 32 only).
     """
     L = lib()
     if not cost.is_cuda:
@@ -163,14 +190,23 @@ def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: t
     for t_ in (start, goal, obst):
         if t_.device != dev:
             raise RuntimeError("all planes must live on the same CUDA device")
-    B, _, H, W = cost.shape
-    for t_ in (start, goal, obst):
-        if t_.shape[0] != B or t_.shape[-2:] != (H, W):
-            raise ValueError("plane shapes differ")
+    if start.ndim != 4:
+        raise ValueError("planes are [B,C,H,W]")
+    B, _, H, W = start.shape
+    planes = [("start", start.detach()), ("goal", goal.detach()), ("obst", obst.detach())]
     keep = []
     p = FwdParams()
-    for name, t_ in (("cost", cost.detach()), ("start", start.detach()), ("goal", goal.detach()),
-                     ("obst", obst.detach())):
+    if cost_kind == COST_TAPS:
+        if cost.dtype != torch.float32 or tuple(cost.shape) != (B, H, W, 9) or not cost.is_contiguous():
+            raise ValueError("COST_TAPS expects a contiguous fp32 [B,H,W,9] tensor")
+        keep.append(cost)
+        p.cost, p.cost_stride = cost.data_ptr(), 9 * H * W
+    else:
+        planes.insert(0, ("cost", cost.detach()))
+    for _, t_ in planes:
+        if t_.shape[0] != B or t_.shape[-2:] != (H, W):
+            raise ValueError("plane shapes differ")
+    for name, t_ in planes:
         k, ptr, stride = _plane(t_)
         keep.append(k)
         setattr(p, name, ptr)
@@ -179,27 +215,72 @@ def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: t
     p.B, p.H, p.W = B, H, W
     p.g_ratio, p.one_minus_g_ratio = gr, omg
     p.T = int(T)
-    p.flags = FWD_NO_EARLY_EXIT if no_early_exit else 0
+    p.flags = (FWD_NO_EARLY_EXIT if no_early_exit else 0) | (FWD_PAIR if pair else 0)
+    p.cost_kind, p.cost_scale, p.cost_bias = int(cost_kind), float(cost_scale), float(cost_bias)
+    Bo = 2 * B if pair else B
     ws_bytes = _ws_cache.get((B, H, W))
     if ws_bytes is None:
         ws_bytes = _ws_cache[(B, H, W)] = int(L.nastar_b200_forward_workspace_bytes(B, H, W))
     guard = contextlib.nullcontext() if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
     with guard:
-        hist = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
-        paths = torch.empty((B, 1, H, W), dtype=torch.int64, device=dev)
-        counters = torch.empty((2, B), dtype=torch.int32, device=dev)   # [t_solve | n_steps]
+        hist = torch.empty((Bo, 1, H, W), dtype=torch.float32, device=dev)
+        paths = torch.empty((Bo, 1, H, W), dtype=torch.int64, device=dev)
+        counters = torch.empty((4 if want_counts else 2, Bo), dtype=torch.int32, device=dev)   # [t_solve | n_steps | ...]
         t_solve, n_steps = counters[0], counters[1]
-        trace = torch.empty((B, int(T)), dtype=torch.int32, device=dev) if want_trace else None
+        trace = torch.empty((Bo, int(T)), dtype=torch.int32, device=dev) if want_trace else None
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev) if ws_bytes else None
         p.histories, p.paths = hist.data_ptr(), paths.data_ptr()
         p.t_solve, p.n_steps = t_solve.data_ptr(), n_steps.data_ptr()
+        if want_counts:
+            p.n_closed, p.path_len = counters[2].data_ptr(), counters[3].data_ptr()
         p.trace = trace.data_ptr() if want_trace else None
         p.workspace = ws.data_ptr() if ws is not None else None
         p.workspace_bytes = ws_bytes
         stream = torch.cuda.current_stream(dev).cuda_stream
         _check(L.nastar_b200_forward(ctypes.byref(p), ctypes.c_void_p(stream)), "nastar_b200_forward")
     del keep
+    if want_counts:
+        return hist, paths, t_solve, n_steps, trace, SearchCounts((counters[2], counters[3]))
     return hist, paths, t_solve, n_steps, trace
+
+
+def pack_inputs(map_designs: torch.Tensor, start: torch.Tensor, goal: torch.Tensor) -> torch.Tensor:
+    """Encoder input of NeuralAstar.encode (reference astar.py:172-177) in ONE kernel: channels-last
+    [B, C+1, Hm, Wm] = cat(map_designs, nearest-upsampled(start + goal))."""
+    L = lib()
+    if not map_designs.is_cuda or map_designs.dtype != torch.float32:
+        raise RuntimeError("pack_inputs: fp32 CUDA tensors only")
+    B, C, Hm, Wm = map_designs.shape
+    H, W = start.shape[-2], start.shape[-1]
+    md = map_designs.detach().contiguous()
+    ks, ps, ss = _plane(start.detach())
+    kg, pg, sg = _plane(goal.detach())
+    dev = map_designs.device
+    guard = contextlib.nullcontext() if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+    with guard:
+        out = torch.empty((B, Hm, Wm, C + 1), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(L.nastar_b200_pack_inputs(md.data_ptr(), C, Hm, Wm, ps, ss, pg, sg, B, H, W, out.data_ptr(),
+                                         ctypes.c_void_p(stream)), "nastar_b200_pack_inputs")
+    del ks, kg
+    return out.permute(0, 3, 1, 2)   # logical NCHW view with channels-last strides
+
+
+def cost_from_taps(taps: torch.Tensor, bias: float, scale: float) -> torch.Tensor:
+    """cost maps [B,1,H,W] = sigmoid(bias + 9-tap gather(taps)) * scale; taps is fp32 [B,H,W,9] (the same
+    arithmetic as the search kernel's COST_TAPS prologue)."""
+    L = lib()
+    B, H, W, nine = taps.shape
+    if nine != 9 or taps.dtype != torch.float32 or not taps.is_contiguous() or not taps.is_cuda:
+        raise ValueError("cost_from_taps expects a contiguous fp32 CUDA [B,H,W,9] tensor")
+    dev = taps.device
+    guard = contextlib.nullcontext() if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+    with guard:
+        cost = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(L.nastar_b200_cost_from_taps(taps.data_ptr(), B, H, W, float(bias), float(scale), cost.data_ptr(),
+                                            ctypes.c_void_p(stream)), "nastar_b200_cost_from_taps")
+    return cost
 
 
 def batch_steps(t_solve: torch.Tensor, n_steps: torch.Tensor, T: int) -> torch.Tensor:

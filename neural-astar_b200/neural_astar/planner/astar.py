@@ -3,8 +3,14 @@
 API contract mirrored from /root/reference/src/neural_astar/planner/astar.py (:17-102 VanillaAstar,
 :105-213 NeuralAstar): constructor keywords, the `.astar` / `.encoder` attributes, `encode()`,
 `perform_astar()` and `forward()` returning `AstarOutput`.  `use_differentiable_astar=False` used to
-select a CPU heap A* (`pq_astar`); both settings are now served by the same GPU search — the
-reference's own test pins the two to identical outputs (tests/astar_test.py:33-42).
+select a CPU heap A* (`pq_astar`); both settings are now served by the same GPU search — identical for
+uniform costs, which is what the reference's own test pins (tests/astar_test.py:33-42); see
+planner/pq_astar.py for the cost-convention difference with learned costs.
+
+Inference hand-off: in eval / no-grad mode on CUDA, `NeuralAstar.forward` runs
+`pack_inputs` (one kernel: start+goal add, nearest upsample, concat, NHWC) -> the encoder's cuDNN convs ->
+the head's skinny GEMM -> the search kernel, whose prologue finishes the encoder (9-tap gather + bias,
+sigmoid, * const: encoder.py:32-34) — no ATen glue launches in between.
 """
 from __future__ import annotations
 
@@ -14,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import _native
 from . import encoder as _encoders
 from .differentiable_astar import AstarOutput, DifferentiableAstar
 from .pq_astar import pq_astar  # noqa: F401  re-exported, like the reference module does
@@ -76,16 +83,68 @@ class NeuralAstar(VanillaAstar):
     def encode(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor) -> torch.Tensor:
         """Cost maps from the encoder; with a "+" input the start/goal marks ride along as an extra channel,
         nearest-upsampled when the image is larger than the planning grid (reference :154-180)."""
+        return self.encoder(self._encoder_input(map_designs, start_maps, goal_maps))
+
+    def _encoder_input(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor) -> torch.Tensor:
         x = map_designs
         if "+" in self.encoder_input:
+            if self.encoder.fast_path_ok(x) and start_maps.is_cuda and start_maps.dtype == torch.float32:
+                return _native.pack_inputs(x, start_maps, goal_maps)    # one kernel, channels-last result
             marks = start_maps + goal_maps
             if marks.shape[-1] != x.shape[-1]:
                 marks = F.interpolate(marks, size=x.shape[-2:], mode="nearest")
             x = torch.cat((x, marks), dim=1)
-        return self.encoder(x)
+        return x
 
     def forward(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor,
                 store_intermediate_results: bool = False) -> AstarOutput:
-        cost_maps = self.encode(map_designs, start_maps, goal_maps)
         passable = torch.ones_like(start_maps) if self.learn_obstacles else map_designs
+        fused = self._fused_forward(map_designs, start_maps, goal_maps, passable, store_intermediate_results)
+        if fused is not None:
+            return fused
+        cost_maps = self.encode(map_designs, start_maps, goal_maps)
         return self.perform_astar(cost_maps, start_maps, goal_maps, passable, store_intermediate_results)
+
+    def forward_pair(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor,
+                     vanilla_g_ratio: float = 0.5):
+        """Validation pair (reference utils/training.py:63-87) in one search launch: returns
+        (outputs of this planner, outputs of VanillaAstar on the same batch, (n_closed [2B], path_len [2B]))
+        or None when the single-launch form does not apply (autograd on, CPU tensors, learn_obstacles, different
+        g_ratio for the baseline, g_ratio < 0.5 batches, pq_astar).  Inference only."""
+        B = start_maps.shape[0]
+        if (torch.is_grad_enabled() or not start_maps.is_cuda or self.learn_obstacles or map_designs.shape[1] != 1
+                or not self.use_differentiable_astar or float(vanilla_g_ratio) != float(self.g_ratio)
+                or (float(self.g_ratio) < 0.5 and B > 1) or map_designs.shape[-2:] != start_maps.shape[-2:]
+                or map_designs.dtype != torch.float32 or start_maps.dtype != torch.float32):
+            return None
+        H, W = start_maps.shape[-2], start_maps.shape[-1]
+        T = self.astar.num_steps(W)
+        kw = {}
+        cost = None
+        if H <= 32 and W <= 32 and self.encoder.fast_path_ok(map_designs):
+            head = self.encoder.head_taps(self._encoder_input(map_designs, start_maps, goal_maps))
+            if head is not None:
+                cost, bias, scale = head
+                kw = dict(cost_kind=_native.COST_TAPS, cost_bias=bias, cost_scale=scale)
+        if cost is None:
+            cost = self.encode(map_designs, start_maps, goal_maps)
+        hist, paths, _, _, _, counts = _native.forward(cost, start_maps, goal_maps, map_designs, float(self.g_ratio), T,
+                                                       pair=True, want_counts=True, **kw)
+        return (AstarOutput(hist[:B], paths[:B], []), AstarOutput(hist[B:], paths[B:], []), tuple(counts))
+
+    def _fused_forward(self, map_designs, start_maps, goal_maps, passable, store_intermediate_results):
+        """Inference fast path: the search kernel consumes the encoder's 9-tap partial products directly
+        (NASTAR_COST_TAPS), so no cost plane, sigmoid, bias add or layout conversion is launched.  Returns None
+        when it does not apply (training / autograd, CPU tensors, planning grids above 32x32, encoders without a
+        single-output-channel conv head, g_ratio < 0.5 batches, pq_astar)."""
+        H, W = start_maps.shape[-2], start_maps.shape[-1]
+        if (not self.use_differentiable_astar or not self.encoder.fast_path_ok(map_designs) or H > 32 or W > 32
+                or not start_maps.is_cuda or (float(self.g_ratio) < 0.5 and start_maps.shape[0] > 1)
+                or start_maps.dtype != torch.float32 or passable.dtype != torch.float32):
+            return None
+        head = self.encoder.head_taps(self._encoder_input(map_designs, start_maps, goal_maps))
+        if head is None or head[0].shape[1:3] != (H, W):
+            return None
+        taps, bias, scale = head
+        return self.astar.search_from_taps(taps, bias, scale, start_maps, goal_maps, passable,
+                                           store_intermediate_results)

@@ -146,6 +146,23 @@ class DifferentiableAstar(nn.Module):
         return AstarOutput(hist, paths, intermediate_results)
 
 
+    def search_from_taps(self, taps: torch.Tensor, bias: float, scale: float, start_maps: torch.Tensor,
+                         goal_maps: torch.Tensor, obstacles_maps: torch.Tensor,
+                         store_intermediate_results: bool = False) -> AstarOutput:
+        """Inference-only entry of the fused encoder hand-off: `taps` [B,H,W,9] are the
+        partial products of the encoder's last 3x3 conv; the kernel prologue computes
+        cost = sigmoid(bias + gather(taps)) * scale (encoder.py:32-34) and searches on it.  No autograd."""
+        W = start_maps.shape[-1]
+        T = self.num_steps(W)
+        hist, paths, t_solve, n_steps, trace = _native.forward(
+            taps, start_maps, goal_maps, obstacles_maps, float(self.g_ratio), T, bool(store_intermediate_results),
+            cost_kind=_native.COST_TAPS, cost_scale=scale, cost_bias=bias)
+        frames: List[dict] = []
+        if store_intermediate_results:
+            frames = _materialise_frames(hist, paths, goal_maps, t_solve, n_steps, trace, T)
+        return AstarOutput(hist, paths, frames)
+
+
 def _coupled_steps(cost_maps, start_maps, goal_maps, obstacles_maps, g_ratio: float, T: int):
     """(T_batch, goal_clamped[B]) for g_ratio < 0.5: the number of iterations the reference's loop executes when
     solved maps keep evolving, and per map whether its goal is selected more than once within them — then

@@ -7,10 +7,17 @@ CNNDownSize) in between, trailing activation(s) dropped; output = sigmoid(model(
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
 import torch.nn as nn
+
+# Precision of the eval fast path's 3x3 convolutions: TF32 tensor-core math (what torch's own default
+# `torch.backends.cudnn.allow_tf32 = True` gives the reference on any Ampere+ GPU) or full fp32.  The head
+# (last, single-output-channel conv) is always fp32.  bench.py states this in its `dtype` field;
+# tests/test_gpu_module_api.py counts how many search masks differ between the two settings.
+ALLOW_TF32 = os.environ.get("NASTAR_B200_ENCODER_TF32", "1") != "0"
 
 
 class EncoderBase(nn.Module):
@@ -22,24 +29,62 @@ class EncoderBase(nn.Module):
         self._plan = None       # cached inference plan (folded weights) for the cuDNN fast path
         self._plan_key = None
         self._nhwc = False      # conv weights converted to channels-last (done lazily on the first CUDA batch)
+        self._head_scalars = (0.0, 1.0)   # (folded bias of the head conv, const) as Python floats
 
     def construct_encoder(self, input_dim: int, encoder_depth: int) -> nn.Module:
         raise NotImplementedError
 
+    def fast_path_ok(self, x: torch.Tensor) -> bool:
+        """Eval-mode, no-grad, fp32 CUDA input: the folded cuDNN plan (and the fused hand-off) may be used."""
+        return (not self.training) and x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32
+
+    def prepare_channels_last(self) -> None:
+        """One-off, explicit: store the conv weights channels-last (cuDNN's tensor-core convolutions are
+        NHWC-native; training step 3.45 -> 2.42 ms on B200).  Pure memory-format change: the Parameter objects,
+        shapes and state-dict contents are unchanged.  Call it once after moving the module to the GPU — before
+        wrapping it in DDP or capturing a CUDA graph.  forward() calls it on the first CUDA batch otherwise."""
+        if not self._nhwc and isinstance(self.model, nn.Sequential):
+            self.model.to(memory_format=torch.channels_last)
+            self._nhwc = True
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if (not self.training) and x.is_cuda and not torch.is_grad_enabled() and x.dtype == torch.float32:
+        if self.fast_path_ok(x):
+            head = self.head_taps(x)
+            if head is not None:
+                # sigmoid(.)*const finished by the engine's glue kernel: the very arithmetic the fused search
+                # prologue performs (NASTAR_COST_TAPS), so encode() and the fused forward agree bit for bit
+                from .. import _native
+
+                taps, bias, scale = head
+                return _native.cost_from_taps(taps, bias, scale)
             plan = self._inference_plan(x.device)
             if plan is not None:
                 return torch.sigmoid(_run_plan(plan, x)) * self.const
         if x.is_cuda and x.dim() == 4 and isinstance(self.model, nn.Sequential):
-            # cuDNN's tensor-core convolutions are NHWC-native: keep weights and activations channels-last so
-            # no layout transposes are launched around every conv (training step 3.45 -> 2.42 ms on B200).
-            # Pure memory-format change: parameter objects, shapes and state-dict contents are unchanged.
-            if not self._nhwc:
-                self.model.to(memory_format=torch.channels_last)
-                self._nhwc = True
+            self.prepare_channels_last()
             x = x.contiguous(memory_format=torch.channels_last)
         return torch.sigmoid(self.model(x)) * self.const
+
+    def head_taps(self, x: torch.Tensor, out: Optional[torch.Tensor] = None):
+        """Eval fast path up to (not including) the 9-tap gather of the single-output-channel head:
+        returns (taps [B,H,W,9] fp32 contiguous, folded bias, const) as (tensor, float, float), or None when the
+        encoder does not end in such a head.  bias/const are cached Python floats (no host sync per call)."""
+        plan = self._inference_plan(x.device)
+        if plan is None or plan[-1][7] is None:
+            return None
+        x = x.contiguous(memory_format=torch.channels_last)
+        with _conv_flags():
+            x = _run_plan_inner(plan[:-1], x)
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        wm = plan[-1][7][0]
+        B, C, H, W = x.shape
+        a = x.permute(0, 2, 3, 1).reshape(-1, C)
+        if out is not None:     # write the GEMM result straight into a caller-owned [B,H,W,9] buffer
+            taps = torch.mm(a, wm, out=out.view(-1, 9)).view(B, H, W, 9)
+        else:
+            taps = torch.mm(a, wm).view(B, H, W, 9)
+        return taps, self._head_scalars[0], self._head_scalars[1]
 
     # ---- eval-mode cuDNN fast path (SURVEY 8(f) rank 3: encoder -> search hand-off) -----------------
     # Still plain PyTorch/cuDNN: BatchNorm (running stats) is folded into the preceding conv, activations
@@ -49,6 +94,8 @@ class EncoderBase(nn.Module):
         if not isinstance(self.model, nn.Sequential):
             return None
         tensors = [t for t in list(self.model.parameters()) + list(self.model.buffers())]
+        if isinstance(self.const, torch.Tensor):
+            tensors.append(self.const)
         key = (str(device),) + tuple((t.data_ptr(), t._version) for t in tensors)
         if key == self._plan_key:
             return self._plan
@@ -82,15 +129,26 @@ class EncoderBase(nn.Module):
                         taps[0, k, k // 3, k % 3] = 1.0
                     head = (w[0].reshape(w.shape[1], 9).contiguous(), taps)
             plan.append((w, b, conv.stride, conv.padding, conv.dilation, relu, pool, head))
+        # scalars of the fused hand-off, read back once per weight version (one host sync at plan build)
+        last_bias = plan[-1][1]
+        self._head_scalars = (float(last_bias.reshape(-1)[0]) if last_bias.numel() == 1 else 0.0,
+                              float(self.const) if not isinstance(self.const, float) else self.const)
         self._plan, self._plan_key = plan, key
         return plan
 
 
+def _conv_flags():
+    """cuDNN settings of the eval fast path.  Inference shapes are static, so cuDNN may time its candidates once
+    per shape instead of trusting the heuristic (which picks a 2x slower kernel for the 64->128 layer on sm_100) —
+    unless the user asked for determinism (set_global_seeds(), utils/training.py): autotuned algorithm choice can
+    differ run to run, so `torch.backends.cudnn.deterministic = True` is honoured and turns autotuning off."""
+    det = bool(torch.backends.cudnn.deterministic)
+    return torch.backends.cudnn.flags(enabled=True, benchmark=not det, deterministic=det, allow_tf32=ALLOW_TF32)
+
+
 def _run_plan(plan, x: torch.Tensor) -> torch.Tensor:
     x = x.contiguous(memory_format=torch.channels_last)
-    # inference shapes are static: let cuDNN time its candidates once per shape instead of trusting the
-    # heuristic (which picks a 2x slower kernel for the 64->128 layer on sm_100)
-    with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=True):
+    with _conv_flags():
         return _run_plan_inner(plan, x)
 
 
@@ -100,7 +158,8 @@ def _conv3x3_single_output(x: torch.Tensor, wm: torch.Tensor, taps: torch.Tensor
     out[n,y,x] = b + sum_k t[n, y+ky-1, x+kx-1, k] (a 9->1 one-hot 3x3 convolution, kept in full fp32)."""
     B, C, H, W = x.shape
     t = (x.permute(0, 2, 3, 1).reshape(-1, C) @ wm).view(B, H, W, 9).permute(0, 3, 1, 2)
-    with torch.backends.cudnn.flags(enabled=True, benchmark=True, deterministic=False, allow_tf32=False):
+    det = bool(torch.backends.cudnn.deterministic)
+    with torch.backends.cudnn.flags(enabled=True, benchmark=not det, deterministic=det, allow_tf32=False):
         return torch.nn.functional.conv2d(t, taps, b, padding=1)
 
 

@@ -59,6 +59,19 @@ def planner_metrics(outputs, va_outputs):
     return float(p_opt), float(p_exp), float(h_mean)
 
 
+def planner_metrics_from_counts(n_closed: torch.Tensor, path_len: torch.Tensor):
+    """(p_opt, p_exp, h_mean) from the per-map counts a NASTAR_FWD_PAIR launch wrote: entries [0,B) belong to the
+    learned-cost search, [B,2B) to vanilla A* on the same problems (the same formulas as planner_metrics /
+    reference :71-85, without reducing the B x H x W masks again)."""
+    B = n_closed.numel() // 2
+    exp_out, exp_ref = n_closed[:B].double(), n_closed[B:].double()
+    p_opt = (path_len[:B] == path_len[B:]).double().mean()
+    p_exp = ((exp_ref - exp_out) / exp_ref).clamp_min(0.0).mean()
+    h_mean = 2.0 / (1.0 / (p_opt + 1e-10) + 1.0 / (p_exp + 1e-10))
+    vals = torch.stack((p_opt, p_exp, h_mean)).tolist()    # one device->host read for the three scalars
+    return vals[0], vals[1], vals[2]
+
+
 class PlannerModule(_ModuleBase):
     def __init__(self, planner, config):
         super().__init__()
@@ -79,12 +92,26 @@ class PlannerModule(_ModuleBase):
         return loss
 
     def validation_step(self, val_batch, batch_idx):
-        loss, outputs = self._loss(val_batch)
-        self._record("metrics/val_loss", loss)
-        map_designs, start_maps, goal_maps = val_batch[:3]
-        if map_designs.shape[1] == 1:  # single-channel maps = shortest-path problems with an A* baseline
-            p_opt, p_exp, h_mean = planner_metrics(outputs, self.vanilla_astar(map_designs, start_maps, goal_maps))
-            for name, value in (("p_opt", p_opt), ("p_exp", p_exp), ("h_mean", h_mean)):
+        map_designs, start_maps, goal_maps, opt_trajs = val_batch
+        pair = None
+        if map_designs.shape[1] == 1 and hasattr(self.planner, "forward_pair") and not torch.is_grad_enabled():
+            # the learned-cost search and the vanilla baseline of this batch in ONE launch, metrics
+            # from the per-map counts the kernel wrote (reference :63-87 runs two planners and reduces in NumPy)
+            pair = self.planner.forward_pair(map_designs, start_maps, goal_maps,
+                                             vanilla_g_ratio=self.vanilla_astar.g_ratio)
+        if pair is not None:
+            outputs, _, counts = pair
+            loss = nn.functional.l1_loss(outputs.histories, opt_trajs)
+            self._record("metrics/val_loss", loss)
+            metrics = planner_metrics_from_counts(*counts)
+        else:
+            loss, outputs = self._loss(val_batch)
+            self._record("metrics/val_loss", loss)
+            metrics = None
+            if map_designs.shape[1] == 1:  # single-channel maps = shortest-path problems with an A* baseline
+                metrics = planner_metrics(outputs, self.vanilla_astar(map_designs, start_maps, goal_maps))
+        if metrics is not None:
+            for name, value in zip(("p_opt", "p_exp", "h_mean"), metrics):
                 self._record(f"metrics/{name}", value)
         return loss
 

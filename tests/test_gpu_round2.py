@@ -1,0 +1,363 @@
+"""GPU tests of the round-2 additions, all through the C ABI of libnastar_b200.so:
+
+  * engine 5 (csrc/nastar_bin16.cuh, binary-cost maps, CTA per map) vs the SPEC oracle, incl. the maps it must
+    hand back to the generic engine (non-binary aliased costs) and the edge cases of the other engines;
+  * NASTAR_FWD_PAIR (validation pair in one launch) and the per-map counts;
+  * the fused encoder hand-off: pack_inputs, NASTAR_COST_LOGIT / NASTAR_COST_TAPS prologues, sigmoid bit-exactness
+    against torch.sigmoid, NeuralAstar's fused forward vs the unfused composition;
+  * GraphedPlanner.replay_host and PipelinedPlanner vs the eager call;
+  * validation metrics from one launch vs the two-call path and the reference's anchors.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def native():
+    from neural_astar import _native
+
+    _native.lib()
+    return _native
+
+
+def _cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _corner_problem(rng, B, H, W, p_obst=0.2):
+    obst = (rng.rand(B, 1, H, W) > p_obst).astype(np.float32)
+    start = np.zeros((B, 1, H, W), np.float32)
+    goal = np.zeros((B, 1, H, W), np.float32)
+    for b in range(B):
+        ys, xs = rng.randint(max(1, H // 4)), rng.randint(max(1, W // 4))
+        yg, xg = H - 1 - rng.randint(max(1, H // 4)), W - 1 - rng.randint(max(1, W // 4))
+        obst[b, 0, ys, xs] = obst[b, 0, yg, xg] = 1
+        start[b, 0, ys, xs] = 1
+        goal[b, 0, yg, xg] = 1
+    return obst, start, goal
+
+
+def _ckpt_planner():
+    from neural_astar.planner import NeuralAstar
+
+    state = np.load(os.path.join(ROOT, "tests", "golden", "mazes032_ckpt_planner_state.npz"))
+    na = NeuralAstar(encoder_arch="CNN")
+    na.load_state_dict({k: torch.from_numpy(state[k]) for k in state.files})
+    return na.cuda().eval()
+
+
+# ------------------------------------------------------------------------------------------------ engine 5
+@pytest.mark.parametrize("H,W,B", [(256, 256, 6), (128, 128, 8), (97, 131, 4), (200, 300, 3), (65, 40, 5), (300, 70, 3)])
+def test_bin16_engine_vs_oracle(native, oracle, H, W, B):
+    """Binary aliased cost planes run on engine 5; outputs (incl. solve step and step count) equal the oracle's."""
+    assert native.lib().nastar_b200_bin16_supported(H, W) == 1
+    rng = np.random.RandomState(7 * H + W)
+    obst, start, goal = _corner_problem(rng, B, H, W)
+    ref = oracle.forward(obst, start, goal, obst, mode="spec")
+    c = _cu(obst)
+    before = native.launch_count()
+    hist, paths, ts, ns, _, (ncl, plen) = native.forward(c, _cu(start), _cu(goal), c, 0.5, W * W, want_counts=True)
+    assert native.launch_count() - before == 2          # engine 5 + the (empty) redo pass of the generic engine
+    np.testing.assert_array_equal(ts.cpu().numpy(), ref.t_solve)
+    np.testing.assert_array_equal(ns.cpu().numpy(), ref.n_steps)
+    np.testing.assert_array_equal(hist.cpu().numpy(), ref.histories)
+    np.testing.assert_array_equal(paths.cpu().numpy(), ref.paths)
+    np.testing.assert_array_equal(ncl.cpu().numpy(), ref.histories.sum((1, 2, 3)).astype(np.int64))
+    np.testing.assert_array_equal(plen.cpu().numpy(), ref.paths.sum((1, 2, 3)))
+
+
+def test_bin16_edge_cases_and_redo(native, oracle):
+    """Unreachable goal, start == goal, start on an obstacle cell, g_ratio != 0.5, a step cap, and a batch in which
+    some maps carry non-binary costs (those are re-run by the generic engine inside the same call)."""
+    H, W, B = 96, 128, 8
+    rng = np.random.RandomState(5)
+    obst, start, goal = _corner_problem(rng, B, H, W, p_obst=0.25)
+    # map 0: goal walled in
+    gy, gx = np.argwhere(goal[0, 0])[0]
+    obst[0, 0, max(gy - 1, 0):gy + 2, max(gx - 1, 0):gx + 2] = 0
+    obst[0, 0, gy, gx] = 1
+    # map 1: start == goal
+    goal[1] = start[1]
+    # map 2: start on an obstacle cell (cost 0 there)
+    sy, sx = np.argwhere(start[2, 0])[0]
+    obst[2, 0, sy, sx] = 0
+    # maps 5..7: non-binary values in the aliased plane -> handed to the generic engine
+    cost = obst.copy()
+    cost[5:] *= (0.5 + rng.rand(3, 1, H, W)).astype(np.float32)
+    for g_ratio, T in ((0.5, W * W), (0.7, W * W), (0.5, 300)):
+        ref = oracle.forward(cost, start, goal, cost, g_ratio=g_ratio, mode="spec", T=T)
+        c = _cu(cost)
+        hist, paths, ts, ns, _ = native.forward(c, _cu(start), _cu(goal), c, g_ratio, T)
+        np.testing.assert_array_equal(ts.cpu().numpy(), ref.t_solve)
+        np.testing.assert_array_equal(ns.cpu().numpy(), ref.n_steps)
+        np.testing.assert_array_equal(hist.cpu().numpy(), ref.histories)
+        solved = ref.t_solve != -2
+        np.testing.assert_array_equal(paths.cpu().numpy()[solved], ref.paths[solved])
+    assert ref.t_solve[0] == -2 or T == 300
+
+
+def test_bin16_matches_generic_engine_on_config5_maps(native):
+    """Config-5-style maps (256x256, 20 % obstacles, far apart start/goal): engine 5 and engine 3 agree bit for bit
+    (the same inputs, non-aliased, take the generic path)."""
+    H = W = 256
+    rng = np.random.RandomState(11)
+    obst, start, goal = _corner_problem(rng, 12, H, W)
+    c, s, g = _cu(obst), _cu(start), _cu(goal)
+    a = native.forward(c, s, g, c, 0.5, W * W)
+    b = native.forward(c.clone(), s, g, c, 0.5, W * W)      # different pointer for cost: not aliased
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+
+
+# ------------------------------------------------------------------------------------------------ pair + counts
+@pytest.mark.parametrize("H,W", [(32, 32), (20, 12), (64, 64), (96, 80)])
+def test_pair_launch_equals_two_calls(native, H, W):
+    rng = np.random.RandomState(H * 3 + W)
+    B = 9
+    obst, start, goal = _corner_problem(rng, B, H, W)
+    cost = (obst * (0.2 + rng.rand(B, 1, H, W))).astype(np.float32)
+    c, s, g, o = _cu(cost), _cu(start), _cu(goal), _cu(obst)
+    before = native.launch_count()
+    hist, paths, ts, ns, _, (ncl, plen) = native.forward(c, s, g, o, 0.5, W * W, pair=True, want_counts=True)
+    n_launch = native.launch_count() - before
+    if H <= 32 and W <= 32:
+        assert n_launch == 1                      # both searches in ONE kernel launch
+    learned = native.forward(c, s, g, o, 0.5, W * W)
+    vanilla = native.forward(o, s, g, o, 0.5, W * W)
+    assert hist.shape[0] == 2 * B
+    for k in range(4):
+        assert torch.equal((hist, paths, ts, ns)[k][:B], learned[k])
+        assert torch.equal((hist, paths, ts, ns)[k][B:], vanilla[k])
+    np.testing.assert_array_equal(ncl.cpu().numpy(), hist.sum((1, 2, 3)).long().cpu().numpy())
+    np.testing.assert_array_equal(plen.cpu().numpy(), paths.sum((1, 2, 3)).cpu().numpy())
+
+
+def test_validation_step_one_launch_matches_two_calls_and_reference_anchor():
+    """PlannerModule.validation_step issues ONE search launch for the learned + vanilla pair; its
+    metrics equal the two-call formulas and the reference's checkpoint anchor (p_opt 0.80 / p_exp 0.445 / h_mean
+    0.572 on the test split)."""
+    from types import SimpleNamespace
+
+    from neural_astar import _native
+    from neural_astar.planner import VanillaAstar
+    from neural_astar.utils.training import PlannerModule, planner_metrics
+
+    g = Golden("mazes032_vanilla_test")
+    na = _ckpt_planner()
+    mod = PlannerModule(na, SimpleNamespace(params=SimpleNamespace(lr=1e-3))).cuda().eval()
+    maps, start, goal = (_cu(x) for x in (g.obst, g.start, g.goal))
+    opt = torch.zeros_like(start)
+    with torch.no_grad():
+        mod.validation_step((maps, start, goal, opt), 0)          # warm-up (plan building, autotuning)
+        before = _native.launch_count()
+        mod.validation_step((maps, start, goal, opt), 0)
+        # pack_inputs + ONE search launch (both halves)
+        assert _native.launch_count() - before == 2
+        got = tuple(mod.logged[f"metrics/{k}"] for k in ("p_opt", "p_exp", "h_mean"))
+        out = na(maps, start, goal)
+        va = VanillaAstar().cuda()(maps, start, goal)
+    want = planner_metrics(out, va)
+    assert got == pytest.approx(want, abs=1e-9)
+    assert abs(got[0] - 0.80) <= 0.03 and abs(got[1] - 0.445) <= 0.02 and abs(got[2] - 0.572) <= 0.02
+    np.testing.assert_array_equal(va.histories.cpu().numpy() != 0, g.bits("hist_bits") != 0)
+
+
+# ------------------------------------------------------------------------------------------------ fused hand-off
+def test_sigmoid_prologue_is_bit_exact_with_torch(native):
+    """NASTAR_COST_LOGIT / cost_from_taps reproduce torch.sigmoid(x) * const bit for bit (encoder.py:32-34)."""
+    torch.manual_seed(0)
+    B, H, W = 7, 32, 32
+    x = torch.cat([torch.randn(B, 1, H, W) * 4, torch.tensor([0.0, -0.0, 88.0, -88.0, 104.0, -104.0, 1e-8, -20.0] * 128)
+                   .reshape(1, 1, H, W)]).cuda()
+    for scale in (1.0, 10.0, 0.37):
+        want = torch.sigmoid(x) * scale
+        taps = torch.zeros((B + 1, H, W, 9), device="cuda")
+        taps[..., 4] = x[:, 0]
+        got = native.cost_from_taps(taps, 0.0, scale)
+        assert torch.equal(got, want)
+
+
+def test_cost_kinds_equal_plane_search(native):
+    rng = np.random.RandomState(3)
+    for (H, W) in ((32, 32), (12, 12), (20, 31)):
+        B = 6
+        obst, start, goal = _corner_problem(rng, B, H, W, p_obst=0.1)
+        s, g, o = _cu(start), _cu(goal), _cu(obst)
+        logits = torch.from_numpy(rng.randn(B, 1, H, W).astype(np.float32) * 2).cuda()
+        taps = torch.from_numpy(rng.randn(B, H, W, 9).astype(np.float32)).cuda()
+        bias, scale = 0.3, 10.0
+        # LOGIT
+        plane = torch.sigmoid(logits) * scale
+        a = native.forward(plane, s, g, o, 0.5, W * W)
+        b = native.forward(logits, s, g, o, 0.5, W * W, cost_kind=native.COST_LOGIT, cost_scale=scale)
+        for x, y in zip(a[:4], b[:4]):
+            assert torch.equal(x, y)
+        # TAPS: the glue kernel and the prologue share one device function; the gather itself is checked against
+        # a plain PyTorch fp32 convolution of the same 9 one-hot taps
+        plane = native.cost_from_taps(taps, bias, scale)
+        w = torch.zeros(1, 9, 3, 3, device="cuda")
+        for k in range(9):
+            w[0, k, k // 3, k % 3] = 1.0
+        with torch.backends.cudnn.flags(enabled=False):
+            ref = torch.sigmoid(torch.nn.functional.conv2d(taps.permute(0, 3, 1, 2), w, padding=1) + bias) * scale
+        assert float((plane - ref).abs().max()) <= 2e-5
+        a = native.forward(plane, s, g, o, 0.5, W * W)
+        b = native.forward(taps, s, g, o, 0.5, W * W, cost_kind=native.COST_TAPS, cost_scale=scale, cost_bias=bias)
+        for x, y in zip(a[:4], b[:4]):
+            assert torch.equal(x, y)
+    with pytest.raises(RuntimeError):      # fused kinds are for H, W <= 32
+        big = torch.zeros((1, 1, 64, 64), device="cuda")
+        native.forward(big, big, big, big, 0.5, 64 * 64, cost_kind=native.COST_LOGIT)
+
+
+@pytest.mark.parametrize("C,Hm,H", [(1, 32, 32), (3, 96, 12), (2, 24, 12), (1, 64, 64)])
+def test_pack_inputs_matches_torch(native, C, Hm, H):
+    torch.manual_seed(C + Hm)
+    B = 5
+    maps = torch.rand(B, C, Hm, Hm, device="cuda")
+    start = torch.zeros(B, 1, H, H, device="cuda")
+    goal = torch.zeros_like(start)
+    for b in range(B):
+        start[b, 0, b % H, (3 * b) % H] = 1
+        goal[b, 0, H - 1 - b % H, H - 1] = 1
+    marks = start + goal
+    if Hm != H:
+        marks = torch.nn.functional.interpolate(marks, size=(Hm, Hm), mode="nearest")
+    want = torch.cat((maps, marks), dim=1)
+    got = native.pack_inputs(maps, start, goal)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("arch,inp,depth,const,shape,hw", [("CNN", "m+", 4, None, (16, 1, 32, 32), 32),
+                                                            ("CNNDownSize", "rgb+", 3, 10.0, (8, 3, 96, 96), 12)])
+def test_fused_forward_equals_unfused_composition(native, arch, inp, depth, const, shape, hw):
+    """NeuralAstar.forward in eval mode (pack kernel -> convs -> head GEMM -> search with the TAPS prologue) gives
+    exactly the outputs of encode() followed by the plain search: the cost arithmetic is one shared device function."""
+    from neural_astar.planner import NeuralAstar
+
+    torch.manual_seed(1)
+    na = NeuralAstar(encoder_input=inp, encoder_arch=arch, encoder_depth=depth, const=const,
+                     learn_obstacles=(arch != "CNN")).cuda()
+    x = (torch.rand(shape, device="cuda") > 0.15).float() if shape[1] == 1 else torch.rand(shape, device="cuda")
+    s = torch.zeros((shape[0], 1, hw, hw), device="cuda"); s[:, :, 0, 0] = 1
+    g = torch.zeros_like(s); g[:, :, -1, -1] = 1
+    if shape[1] == 1:
+        x[:, :, 0, 0] = 1; x[:, :, -1, -1] = 1
+    na.train()
+    for _ in range(2):
+        na.encode(x, s, g)      # non-trivial BatchNorm statistics
+    na.eval()
+    with torch.no_grad():
+        na(x, s, g)             # plan building
+        before = native.launch_count()
+        out = na(x, s, g, store_intermediate_results=False)
+        assert native.launch_count() - before == 2          # pack_inputs + search; the rest is cuDNN/cuBLAS
+        cost = na.encode(x, s, g)
+        passable = torch.ones_like(s) if na.learn_obstacles else x
+        want = na.perform_astar(cost, s, g, passable)
+        frames = na(x, s, g, store_intermediate_results=True)
+    assert torch.equal(out.histories, want.histories) and torch.equal(out.paths, want.paths)
+    assert torch.equal(frames.histories, want.histories) and len(frames.intermediate_results) >= 2
+    # the cost maps themselves agree with the module's own (slow, autograd) path to TF32 accuracy
+    slow = na.encode(x, s, g)
+    assert slow.requires_grad
+    assert float((cost - slow).abs().max()) < 3e-3 * (1.0 if const is None else const)
+
+
+def test_tf32_encoder_mask_differences_are_counted():
+    """how many of the 100 headline maps change their search masks because the encoder's convs
+    run in TF32 (the fast path's default, like torch's own cuDNN default) instead of fp32 — against the reference's
+    CPU outputs for the same checkpoint (mazes032_neural_test).  Prints the counts; bounds them loosely."""
+    import neural_astar.planner.encoder as enc
+
+    g = Golden("mazes032_vanilla_test")
+    gn = Golden("mazes032_neural_test")
+    na = _ckpt_planner()
+    maps, start, goal = (_cu(x) for x in (g.obst, g.start, g.goal))
+    res = {}
+    old = enc.ALLOW_TF32
+    try:
+        for tf32 in (True, False):
+            enc.ALLOW_TF32 = tf32
+            with torch.no_grad():
+                out = na(maps, start, goal)
+                cost = na.encode(maps, start, goal)
+            dh = (out.histories.cpu().numpy() != 0) != (gn.bits("hist_bits") != 0)
+            dp = (out.paths.cpu().numpy() != 0) != (gn.bits("path_bits") != 0)
+            res[tf32] = dict(maps_hist_differ=int(dh.reshape(100, -1).any(1).sum()),
+                             maps_path_differ=int(dp.reshape(100, -1).any(1).sum()),
+                             cells_hist_differ=int(dh.sum()),
+                             max_cost_err=float((cost.cpu() - torch.from_numpy(gn.cost)).abs().max()))
+    finally:
+        enc.ALLOW_TF32 = old
+    print("encoder precision vs reference masks (100 maps):", res)
+    try:    # keep the record (copied to profiles/ by hand): gpurun_out/ travels back from the GPU box
+        import json
+
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "r02_tf32_mask_diff.json"), "w") as f:
+            json.dump({"tf32": res[True], "fp32": res[False]}, f, indent=1)
+    except OSError:
+        pass
+    assert res[False]["max_cost_err"] < 1e-4 and res[True]["max_cost_err"] < 5e-3
+    assert res[False]["maps_hist_differ"] <= 15 and res[True]["maps_hist_differ"] <= 60
+
+
+# ------------------------------------------------------------------------------------------------ graphs / pipeline
+def test_pipelined_and_host_graphs_match_eager():
+    from neural_astar.utils.inference import GraphedPlanner, PipelinedPlanner
+
+    g = Golden("mazes032_vanilla_test")
+    na = _ckpt_planner()
+    maps, start, goal = (_cu(x) for x in (g.obst, g.start, g.goal))
+    torch.manual_seed(0)
+    batches = []
+    for k in range(5):
+        perm = torch.randperm(100, device="cuda")
+        batches.append((maps[perm], start[perm], goal[perm]))
+    with torch.no_grad():
+        want = [na(*b) for b in batches]
+    # device-resident pipeline
+    pipe = PipelinedPlanner(na, maps, start, goal)
+    got = []
+    for b in batches:
+        prev = pipe.submit(*b)
+        if prev is not None:
+            got.append((prev.histories.clone(), prev.paths.clone()))
+    last = pipe.drain()
+    got.append((last.histories.clone(), last.paths.clone()))
+    assert len(got) == 5
+    for (h, p), w in zip(got, want):
+        assert torch.equal(h, w.histories) and torch.equal(p, w.paths)
+    # host pipeline: pinned in, pinned out, copies inside the graphs
+    pipe = PipelinedPlanner(na, maps, start, goal, host=True)
+    results = []
+    for k, b in enumerate(batches):
+        for dst, src in zip(pipe.host_inputs[k % 2], b):
+            dst.copy_(src.cpu())
+        pipe.submit()
+        if k >= 1:
+            torch.cuda.synchronize()
+            results.append(tuple(t.clone() for t in pipe.host_outputs[(k - 1) % 2]))
+    pipe.drain()
+    torch.cuda.synchronize()
+    results.append(tuple(t.clone() for t in pipe.host_outputs[(len(batches) - 1) % 2]))
+    for (h, p), w in zip(results, want):
+        assert torch.equal(h, w.histories.cpu()) and torch.equal(p, w.paths.cpu())
+    # single-graph end-to-end replay
+    fast = GraphedPlanner(na, maps, start, goal)
+    for dst, src in zip(fast.host_inputs, batches[2]):
+        dst.copy_(src.cpu())
+    fast.replay_host()
+    torch.cuda.synchronize()
+    assert torch.equal(fast.host_outputs[0], want[2].histories.cpu())
+    assert torch.equal(fast.host_outputs[1], want[2].paths.cpu())
