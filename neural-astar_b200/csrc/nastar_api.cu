@@ -247,14 +247,18 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
             cudaError_t e = cudaMemsetAsync(ba.queue, 0, 256, stream);
             if (e != cudaSuccess) return cuda_fail(e);
             const size_t bsmem = nastar::Bin16Layout(p->H, p->W).smem_bytes();
-            e = cudaFuncSetAttribute(nastar::astar_bin16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bsmem));
-            if (e != cudaSuccess) return cuda_fail(e);
-            // resident CTAs per SM by shared memory (1 at 256x256, several for smaller maps)
-            int per_sm = int(kMaxDynSmem / (bsmem + 1024));
-            per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-            const int bgrid = p->B < num_sms() * per_sm ? p->B : num_sms() * per_sm;
-            nastar::astar_bin16_kernel<<<bgrid, nastar::kBin16Threads, bsmem, stream>>>(ba);
-            e = cudaGetLastError();
+            auto launch16 = [&](auto kernel) -> cudaError_t {
+                cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bsmem));
+                if (e2 != cudaSuccess) return e2;
+                int per_sm = 1;   // resident CTAs per SM (1 at 256x256, a few for smaller maps)
+                e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nastar::kBin16Threads, bsmem);
+                if (e2 != cudaSuccess) return e2;
+                per_sm = per_sm < 1 ? 1 : per_sm;
+                const int bgrid = p->B < num_sms() * per_sm ? p->B : num_sms() * per_sm;
+                kernel<<<bgrid, nastar::kBin16Threads, bsmem, stream>>>(ba);
+                return cudaGetLastError();
+            };
+            e = (p->H <= 256) ? launch16(nastar::astar_bin16_kernel<8>) : launch16(nastar::astar_bin16_kernel<16>);
             if (e != cudaSuccess) return cuda_fail(e);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             ga.redo = ba.redo;

@@ -19,32 +19,50 @@ _ACTION_TO_MOVE = ((0, -1, 0), (0, 0, +1), (0, 0, -1), (0, +1, 0), (0, -1, +1), 
 _SPLIT_OFFSET = {"train": 0, "valid": 4, "test": 8}
 
 
+def _make_grid(x: torch.Tensor, nrow: int = 8, padding: int = 2) -> torch.Tensor:
+    """torchvision.utils.make_grid(x) with its defaults, without the torchvision dependency: a [B,C,H,W] batch
+    (single-channel images repeated to RGB) tiled 8 per row with a 2-pixel zero border; a batch of ONE image is
+    returned as is, unpadded — exactly like torchvision."""
+    x = x.detach().cpu()
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    if x.shape[1] == 1:
+        x = x.repeat(1, 3, 1, 1)
+    B, C, H, W = x.shape
+    if B == 1:
+        return x[0]
+    xmaps = min(nrow, B)
+    ymaps = -(-B // xmaps)
+    hh, ww = H + padding, W + padding
+    grid = x.new_zeros((C, hh * ymaps + padding, ww * xmaps + padding))
+    for k in range(B):
+        yy, xx = divmod(k, xmaps)
+        grid[:, yy * hh + padding:yy * hh + padding + H, xx * ww + padding:xx * ww + padding + W] = x[k]
+    return grid
+
+
 def visualize_results(map_designs: torch.Tensor, planner_outputs, scale: int = 1) -> np.ndarray:
-    """Tile a batch into one RGB image: map in grey, explored nodes green-ish, path red (reference :16-51)."""
+    """Search results as one uint8 RGB image [Hg, Wg, 3] (reference :16-51): the maps tiled like
+    torchvision's make_grid (8 per row, 2-pixel border), explored nodes painted (0.2, 0.8, 0), path cells
+    (1, 0, 0), values * 255 — the format scripts/create_gif.py hands to moviepy.  `scale` > 1 enlarges with
+    nearest-neighbour resampling (the reference passes (rows*scale, cols*scale) to PIL as (width, height);
+    kept as is)."""
     if isinstance(planner_outputs, dict):
         histories, paths = planner_outputs["histories"], planner_outputs["paths"]
     else:
         histories, paths = planner_outputs.histories, planner_outputs.paths
-    m = map_designs.detach().cpu().float()
-    if m.shape[1] == 1:
-        m = m.repeat(1, 3, 1, 1)
-    h = histories.detach().cpu().float()
-    p = paths.detach().cpu().float()
-    rgb = m.clone()
-    explored = torch.tensor([0.2, 0.8, 0.0]).view(1, 3, 1, 1)
-    on_path = torch.tensor([1.0, 0.0, 0.0]).view(1, 3, 1, 1)
-    rgb = rgb * (1 - h) + explored * h
-    rgb = rgb * (1 - p) + on_path * p
-    B, _, H, W = rgb.shape
-    pad = 2
-    canvas = torch.zeros(3, H + 2 * pad, B * (W + pad) + pad)
-    for b in range(B):
-        x0 = pad + b * (W + pad)
-        canvas[:, pad:pad + H, x0:x0 + W] = rgb[b]
-    img = canvas.permute(1, 2, 0).numpy()
+    results = _make_grid(map_designs.float()).permute(1, 2, 0).clone()
+    h = _make_grid(histories.float()).permute(1, 2, 0)
+    p = _make_grid(paths.float()).permute(1, 2, 0)
+    results[h[..., 0] == 1] = torch.tensor([0.2, 0.8, 0.0])
+    results[p[..., 0] == 1] = torch.tensor([1.0, 0.0, 0.0])
+    results = (results.numpy() * 255.0).astype("uint8")
     if scale > 1:
-        img = np.kron(img, np.ones((scale, scale, 1), dtype=img.dtype))
-    return img
+        from PIL import Image
+
+        results = np.asarray(Image.fromarray(results).resize([x * scale for x in results.shape[:2]],
+                                                             resample=Image.NEAREST))
+    return results
 
 
 class MazeDataset(data.Dataset):

@@ -89,17 +89,35 @@ def test_warcraft_dataset(tmp_path):
     assert float(start[:, 0, 0, 0].sum()) == 4 and float(goal[:, 0, -1, -1].sum()) == 4   # data.py:284-292
 
 
-def test_visualize_results_marks_path_and_history():
+def test_visualize_results_follows_the_reference_convention():
+    """uint8 HxWx3 image laid out like torchvision.utils.make_grid (8 per row, 2-pixel border, values*255) —
+    the frames scripts/create_gif.py feeds to moviepy (reference utils/data.py:16-51)."""
     from neural_astar.planner.differentiable_astar import AstarOutput
     from neural_astar.utils.data import visualize_results
 
-    m = torch.ones(2, 1, 8, 8)
-    h = torch.zeros(2, 1, 8, 8); h[:, :, 2, :] = 1
-    p = torch.zeros(2, 1, 8, 8, dtype=torch.long); p[:, :, 2, 3] = 1
-    img = visualize_results(m, AstarOutput(h, p))
-    assert img.ndim == 3 and img.shape[2] == 3 and img.shape[0] >= 8 and img.shape[1] >= 16
-    assert np.isclose(img, [1.0, 0.0, 0.0]).all(-1).sum() == 2       # one red path cell per map
-    assert visualize_results(m, {"histories": h, "paths": p}, scale=2).shape[0] == 2 * img.shape[0]
+    tv = pytest.importorskip("torchvision.utils")
+    rng = np.random.RandomState(0)
+    for B, scale in ((10, 1), (2, 1), (1, 1), (3, 2)):
+        m = torch.from_numpy((rng.rand(B, 1, 8, 12) > 0.3).astype(np.float32))
+        h = torch.zeros(B, 1, 8, 12); h[:, :, 2, :] = 1
+        p = torch.zeros(B, 1, 8, 12, dtype=torch.long); p[:, :, 2, 3] = 1
+        img = visualize_results(m, AstarOutput(h, p), scale=scale)
+        # the reference's own sequence of operations, written with torchvision
+        want = tv.make_grid(m).permute(1, 2, 0)
+        hh, pp = tv.make_grid(h).permute(1, 2, 0), tv.make_grid(p).permute(1, 2, 0).float()
+        want[hh[..., 0] == 1] = torch.tensor([0.2, 0.8, 0])
+        want[pp[..., 0] == 1] = torch.tensor([1.0, 0.0, 0])
+        want = (want.numpy() * 255.0).astype("uint8")
+        if scale > 1:
+            from PIL import Image
+
+            want = np.asarray(Image.fromarray(want).resize([x * scale for x in want.shape[:2]], resample=Image.NEAREST))
+        assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
+        assert img.shape == want.shape
+        np.testing.assert_array_equal(img, want)
+    assert visualize_results(m, {"histories": h, "paths": p}).dtype == np.uint8
+    big = visualize_results(torch.ones(10, 1, 8, 8), AstarOutput(torch.zeros(10, 1, 8, 8), torch.zeros(10, 1, 8, 8)))
+    assert big.shape == (2 * 10 + 2, 8 * 10 + 2, 3)        # two rows of tiles: 8 + 2
 
 
 def test_training_helpers(tmp_path):
