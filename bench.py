@@ -5,29 +5,33 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload = BASELINE.json configs[1]: NeuralAstar inference (CNN encoder + differentiable A*),
-mazes_032_moore_c8 32x32, batch 100 per GPU.  A "step" is one `planner(map_designs, start_maps,
-goal_maps)` forward over the batch.  Inputs are the reference's test split (100 maps, start
-positions drawn with seed 1234) and the reference's shipped checkpoint, both committed as small
-fixtures under tests/golden/ (generated by tests/golden/make_golden.py).
+mazes_032_moore_c8 32x32, batch 100 per GPU.  A "step" is one `planner(map_designs, start_maps, goal_maps)` forward
+over one batch.  Inputs are the reference's test split (100 maps, start positions drawn with seed 1234) and the
+reference's shipped checkpoint, both committed as small fixtures under tests/golden/ (tests/golden/make_golden.py).
 
-Prints ONE JSON line (rank 0) with the contract keys plus `roofline`, `cpu_baseline`, `e2e`,
-`clocks`, `gpu_launches`.  `--impl reference` times the CPU restatement of the reference's own
-algorithm (oracle/astar_oracle.c, LITERAL form = the dense exp/softmax/argmax loop the
-reference executes) + the same encoder on torch CPU, with all host threads.
+The K timed steps run through `neural_astar.utils.inference.PipelinedPlanner` (public API): one CUDA-graph launch
+per step in which the search kernel of batch k overlaps the encoder convolutions of batch k+1.  `value` = device
+resident inputs (rotated through a ring larger than L2); `e2e` = the same loop with every step's inputs copied from
+pinned host memory and its results copied back (copies inside the graph).  Both are timed with CUDA events around
+the WHOLE K-step loop (pipeline fill and drain included), barrier + synchronize on both sides, max over ranks.
+
+Prints ONE JSON line (rank 0) with the contract keys plus `roofline`, `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches`, and `configs` (BASELINE.json configs[2..4]: training step, WarCraft-shaped 12x12, 256x256).
+`--impl reference` times the reference's own PyTorch CPU implementation of the path when it was staged under
+oracle/_ref (oracle/stage_ref.py), else the C restatement (oracle/astar_oracle.c, LITERAL form) + torch-CPU encoder.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "neural-astar_b200"), os.path.join(ROOT, "tests")):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+PKG = os.path.join(ROOT, "neural-astar_b200")
+REF_STAGE = os.path.join(ROOT, "oracle", "_ref")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -38,16 +42,27 @@ BATCH = 100
 H = W = 32
 N_CELLS = H * W
 ALGO_BYTES_PER_MAP = 28 * N_CELLS  # read cost+start+goal+obstacles, write histories(f32)+paths(i64)
+WORKLOAD = "NeuralAstar inference, mazes_032_moore_c8 32x32, batch=100 (BASELINE.json configs[1])"
+DATA = "mazes_032_moore_c8 test split (100 maps, seed-1234 starts) + shipped checkpoint, committed fixtures"
 
 
-def load_problem():
+def _paths(ours: bool):
+    for p in ((ROOT, PKG, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")) if ours
+              else (ROOT, REF_STAGE, os.path.join(ROOT, "tests"))):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def load_problem(name="mazes032_vanilla_test"):
     from golden_util import Golden
 
-    g = Golden("mazes032_vanilla_test")
+    g = Golden(name)
     return g.obst.astype(np.float32), g.start.astype(np.float32), g.goal.astype(np.float32), g
 
 
 def load_planner(device):
+    """NeuralAstar with the reference's shipped weights — from OUR package, or from the staged reference when the
+    process runs `--impl reference` (sys.path decides which `neural_astar` is imported; never both)."""
     from neural_astar.planner import NeuralAstar
 
     planner = NeuralAstar(encoder_input="m+", encoder_arch="CNN", encoder_depth=4)
@@ -57,61 +72,85 @@ def load_planner(device):
     return planner.to(device).eval()
 
 
+# ------------------------------------------------------------------------------------------------ clocks
+_SAMPLER_SRC = r"""
+import json, sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+samples, reasons = [], set()
+mx = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+print("ready", flush=True)
+import select
+while True:
+    if select.select([sys.stdin], [], [], 0)[0]:
+        break
+    try:
+        samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for bit, nm in names.items():
+            if r & bit:
+                reasons.add(nm)
+    except Exception:
+        pass
+    time.sleep(0.002)
+print(json.dumps({"samples": samples, "reasons": sorted(reasons), "max": mx}), flush=True)
+"""
+
+
 class ClockSampler:
-    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+    """SM clocks / throttle reasons sampled through NVML every 2 ms by a SEPARATE PROCESS while the timed regions
+    run (a polling thread inside this interpreter would compete for the GIL with the launching thread)."""
 
     def __init__(self, index: int):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
-        self._t = None
-        try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-        except Exception:  # pragma: no cover
-            self.nv = None
-
-    def _loop(self):
-        nv = self.nv
-        names = {
-            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-        }
-        while not self._stop.is_set():
-            try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-            except Exception:
-                pass
-            time.sleep(0.002)
+        self.index, self.proc, self.result = index, None, None
 
     def __enter__(self):
-        if self.nv is not None:
-            self._t = threading.Thread(target=self._loop, daemon=True)
-            self._t.start()
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() != "ready":
+                self.proc = None
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        if self._t is not None:
-            self._t.join()
+        if self.proc is not None:
+            try:
+                out, _ = self.proc.communicate("stop\n", timeout=10)
+                self.result = json.loads(out.strip().splitlines()[-1])
+            except Exception:
+                self.result = None
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        r = self.result
+        if not r or not r.get("samples"):
+            return {"sm_mhz": None, "sm_max_mhz": (r or {}).get("max"), "reasons": (r or {}).get("reasons", []), "samples": 0}
+        return {"sm_mhz": float(np.median(r["samples"])), "sm_max_mhz": r["max"], "reasons": r["reasons"],
+                "samples": len(r["samples"]), "sampler": "NVML, separate process, 2 ms period, over all timed legs"}
+
+
+def pin_to_gpu_numa(index: int):
+    """Run this rank on the CPU cores NVML reports as local to its GPU (SCALE_r01: GPU0-3 -> CPUs 0-31,64-95)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def peak_hbm():
@@ -135,112 +174,332 @@ def ncu_traffic():
     return None
 
 
-# ------------------------------------------------------------------------------------------------
-def cpu_reference_step(planner_cpu, maps, start, goal, oracle, threads):
-    """One pass of the reference's CPU path: torch-CPU encoder + LITERAL restatement of the loop."""
-    with torch.no_grad():
-        cost = planner_cpu.encode(torch.from_numpy(maps), torch.from_numpy(start), torch.from_numpy(goal)).numpy()
-    out = oracle.forward(cost, start, goal, maps, g_ratio=0.5, mode="literal")
-    return out
-
-
-def pick_cpu_threads(planner_cpu, maps, start, goal, oracle):
-    """The host's best thread count for this workload: oversubscribing SMT siblings across sockets makes
-    both MKL-DNN and OpenMP collapse (measured on the B200 host: 128 threads 10x slower than 32), so the
-    baseline sweeps a few counts (one pass each, untimed) and keeps the fastest."""
+# ------------------------------------------------------------------------------------------------ reference arm
+def _pick_threads(fn, set_threads):
+    """The host's best thread count: oversubscribing SMT siblings across sockets makes MKL-DNN / OpenMP collapse
+    (measured on the B200 host: 128 threads 10x slower than 32), so a few counts are tried and the fastest kept."""
     ncpu = os.cpu_count() or 1
     cands = sorted({min(ncpu, c) for c in (8, 16, 32, 64, torch.get_num_threads(), ncpu)})
     best, best_t = cands[0], float("inf")
     for c in cands:
-        torch.set_num_threads(c)
-        oracle.set_threads(c)
-        cpu_reference_step(planner_cpu, maps, start, goal, oracle, c)
+        set_threads(c)
+        fn()
         t0 = time.perf_counter()
-        cpu_reference_step(planner_cpu, maps, start, goal, oracle, c)
+        fn()
         dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
         if dt > 4 * best_t:
             break
-    torch.set_num_threads(best)
-    oracle.set_threads(best)
-    return best, cands
-
-
-def run_cpu_baseline(maps, start, goal, budget_s=10.0):
-    """Bounded sample of the same workload on the host cores (rank 0, N=1 only)."""
-    from oracle import oracle
-
-    oracle.build()
-    planner_cpu = load_planner(torch.device("cpu"))
-    threads, cands = pick_cpu_threads(planner_cpu, maps, start, goal, oracle)
-    t0 = time.perf_counter()
-    reps = 0
-    while True:
-        cpu_reference_step(planner_cpu, maps, start, goal, oracle, threads)
-        reps += 1
-        dt = time.perf_counter() - t0
-        if dt > budget_s or reps >= 50:
-            break
-    return {"value": BATCH * reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{reps} passes of the same b={BATCH} batch: torch-CPU encoder + oracle LITERAL loop "
-                      f"(oracle/astar_oracle.c, OpenMP over maps), {dt:.1f} s; thread count {threads} = fastest of "
-                      f"{cands} on {os.cpu_count()} logical CPUs"}
+    set_threads(best)
+    return best, cands, best_t
 
 
 def bench_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference's CPU implementation of the path on this box's host cores, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import oracle
-
-    oracle.build()
+    staged = os.path.isdir(os.path.join(REF_STAGE, "neural_astar", "planner")) and not args.port
+    _paths(ours=False)
     maps, start, goal, _ = load_problem()
-    planner_cpu = load_planner(torch.device("cpu"))
-    threads, cands = pick_cpu_threads(planner_cpu, maps, start, goal, oracle)
-    # bound the whole run (warm-up + K timed steps) to a few minutes: when K full batches would take longer,
-    # every step processes the first m maps of the batch instead (maps/s stays the unit; the sample is stated)
-    t0 = time.perf_counter()
-    cpu_reference_step(planner_cpu, maps, start, goal, oracle, threads)
-    t_full = time.perf_counter() - t0
-    budget_s = 150.0
+    if staged:
+        # the reference's own modules (staged by oracle/stage_ref.py at build time): NeuralAstar.forward =
+        # encoder + the PyTorch DifferentiableAstar loop (differentiable_astar.py:150-267), unmodified
+        import neural_astar
+
+        assert os.path.realpath(neural_astar.__file__).startswith(os.path.realpath(REF_STAGE)), neural_astar.__file__
+        planner = load_planner(torch.device("cpu"))
+        tm, ts, tg = (torch.from_numpy(x) for x in (maps, start, goal))
+
+        def run(m=BATCH):
+            with torch.no_grad():
+                return planner(tm[:m], ts[:m], tg[:m])
+
+        threads, cands, t_full = _pick_threads(run, torch.set_num_threads)
+        kind = "reference"
+        what = "the reference's own PyTorch NeuralAstar.forward (staged, unmodified: encoder + DifferentiableAstar loop)"
+    else:
+        # fallback when nothing was staged: C restatement of the loop (LITERAL form) + torch-CPU encoder of our package
+        _paths(ours=True)
+        from oracle import oracle
+
+        oracle.build()
+        planner = load_planner(torch.device("cpu"))
+
+        class _Out:
+            pass
+
+        def run(m=BATCH):
+            with torch.no_grad():
+                cost = planner.encode(*(torch.from_numpy(x[:m]) for x in (maps, start, goal))).numpy()
+            return oracle.forward(cost, start[:m], goal[:m], maps[:m], g_ratio=0.5, mode="literal")
+
+        def set_threads(c):
+            torch.set_num_threads(c)
+            oracle.set_threads(c)
+
+        threads, cands, t_full = _pick_threads(run, set_threads)
+        kind = "port"
+        what = "torch-CPU encoder + oracle LITERAL loop (oracle/astar_oracle.c, OpenMP over maps)"
+    # bound the whole run (warm-up + K timed steps) to a few minutes: when K full batches would take longer, every
+    # step processes the first m maps of the batch instead (maps/s stays the unit; the sample is stated)
+    budget_s = float(args.budget)
     m = BATCH
-    if t_full * (args.steps + args.warmup) > budget_s:
-        m = int(max(10, min(BATCH, BATCH * budget_s / (t_full * (args.steps + args.warmup)))))
-    maps, start, goal = maps[:m], start[:m], goal[:m]
+    total = args.steps + args.warmup
+    if t_full * total > budget_s:
+        m = int(max(10, min(BATCH, BATCH * budget_s / (t_full * total))))
     out = None
     for _ in range(args.warmup):
-        out = cpu_reference_step(planner_cpu, maps, start, goal, oracle, threads)
+        out = run(m)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = cpu_reference_step(planner_cpu, maps, start, goal, oracle, threads)
+        out = run(m)
     dt = time.perf_counter() - t0
     value = m * args.steps / dt
+    hist_sum = float(out.histories.sum())
+    sample = (f"each step = the first {m} of the b={BATCH} maps through {what}; {threads} threads = fastest of {cands} "
+              f"on {os.cpu_count()} logical CPUs")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "mazes_032_moore_c8 test split (100 maps, seed-1234 starts) + shipped checkpoint, committed fixtures",
-        "config": {"workload": "NeuralAstar inference, mazes_032_moore_c8 32x32, batch=100 (BASELINE.json configs[1])",
-                   "batch_per_gpu": BATCH, "grid": "32x32", "g_ratio": 0.5, "T_max": 1024,
-                   "timing": "host wall clock (CPU implementation)"},
-        "expansions_per_s": float(out.histories.sum()) * args.steps / dt,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"each step = the first {m} of the b={BATCH} maps: torch-CPU encoder + oracle LITERAL "
-                                   f"loop; {threads} threads = fastest of {cands} on {os.cpu_count()} logical CPUs"},
+        "data": DATA,
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "grid": "32x32", "g_ratio": 0.5, "T_max": W * W},
+        "timing": "host wall clock (CPU implementation)",
+        "expansions_per_s": hist_sum * args.steps / dt,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-# ------------------------------------------------------------------------------------------------
-def bench_ours(args):
+def run_cpu_baseline(budget_s=20.0):
+    """cpu_baseline of our own line (rank 0, N=1): the reference arm in a SUBPROCESS (its `neural_astar` package is
+    the staged reference, which must not meet ours in one interpreter), bounded to ~`budget_s` seconds."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5", "--warmup", "1",
+           "--budget", str(budget_s)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout
+        line = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
+        return line["cpu_baseline"]
+    except Exception as e:  # pragma: no cover
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": f"reference arm failed: {e!r}"}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+class Timer:
+    def __init__(self, dist, dev):
+        self.dist, self.dev = dist, dev
+
+    def barrier(self, all_ranks=True):
+        if self.dist is not None and all_ranks:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def loop(self, body, all_ranks=True):
+        """Device time of `body()` as a whole (events on the launching stream), barrier + sync on both sides."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier(all_ranks)
+        a.record()
+        out = body()
+        b.record()
+        self.barrier(all_ranks)
+        return a.elapsed_time(b), out
+
+    def per_step(self, fn, steps, flush):
+        """Sum of per-step event pairs with the L2 flushed (outside the pairs) between steps: rank-local."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        out = None
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            out = fn()
+            b.record()
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in evs]
+        return ts, out
+
+
+def config_c3(dev, peak):
+    """BASELINE.json configs[2]: NeuralAstar training step (scripts/train.py semantics: Tmax=0.25, B=100, RMSprop
+    1e-3, L1 loss) on the reference's first training batch (tests/golden/train_curve_mazes032.npz)."""
+    from types import SimpleNamespace
+
     from neural_astar import _native
+    from neural_astar.planner import NeuralAstar
+    from neural_astar.utils.training import PlannerModule
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "train_curve_mazes032.npz"))
+    B, Hh, Ww = (int(v) for v in z["shape"])
+    N = Hh * Ww
+
+    def bits(k):
+        return np.unpackbits(z[k], axis=1)[:, :N].reshape(B, 1, Hh, Ww).astype(np.float32)
+
+    def onehot(k):
+        x = np.zeros((B, N), np.float32)
+        x[np.arange(B), z[k]] = 1
+        return x.reshape(B, 1, Hh, Ww)
+
+    batch = [torch.from_numpy(x).to(dev) for x in (bits("obst_bits"), onehot("start_idx"), onehot("goal_idx"), bits("opt_bits"))]
+    torch.manual_seed(1234)
+    planner = NeuralAstar(encoder_input="m+", encoder_arch="CNN", encoder_depth=4, Tmax=0.25)
+    module = PlannerModule(planner, SimpleNamespace(params=SimpleNamespace(lr=1e-3))).to(dev).train()
+    opt = module.configure_optimizers()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = module.training_step(batch, 0)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    K = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(K):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / K
+    # the two search kernels alone: forward (T = 256 cap) and closed-form backward, on the current cost maps
+    with torch.no_grad():
+        cost = planner.encode(*batch[:3]).contiguous()
+    T = int(0.25 * Ww * Ww)
+    fw = lambda: _native.forward(cost, batch[1], batch[2], batch[0], 0.5, T)  # noqa: E731
+    hist, _, ts, ns, _ = fw()
+    Tb = _native.batch_steps(ts, ns, T)
+    gh = torch.sign(hist - batch[3]) / hist.numel()
+    bw = lambda: _native.backward(cost, batch[1], batch[2], batch[0], gh, Tb, ts, 0.5)  # noqa: E731
+
+    def t_of(fn):
+        for _ in range(3):
+            fn()
+        x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x.record()
+        for _ in range(10):
+            fn()
+        y.record()
+        torch.cuda.synchronize()
+        return x.elapsed_time(y) / 10 * 1e3
+
+    fwd_us, bwd_us = t_of(fw), t_of(bw)
+    algo = 36 * N * B    # SURVEY 8(d): 28*N forward + read grad_histories + write grad_cost
+    ach = algo / ((fwd_us + bwd_us) * 1e-6) / 1e9
+    return {"workload": "NeuralAstar training step (Tmax=0.25 -> T=256, b=100, RMSprop, L1), mazes_032 first train batch",
+            "train_steps_per_s": 1e3 / ms, "maps_per_s": B * 1e3 / ms, "ms_per_step": ms,
+            "search_fwd_us": fwd_us, "search_bwd_us": bwd_us,
+            "roofline": {"bound": "hbm", "kernel": "astar_warp32_kernel<0,0,0> + <0,1,0>", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": algo}}
+
+
+def config_c4(dev, peak):
+    """BASELINE.json configs[3]: WarCraft-shaped inference, b=512, 96x96 RGB -> 12x12 costs (data not shipped:
+    synthetic RGB as SURVEY.md 8(d) C4 prescribes), CNNDownSize depth 3, const 10, learn_obstacles."""
+    from neural_astar import _native
+    from neural_astar.planner import NeuralAstar
+    from neural_astar.utils.inference import GraphedPlanner
+
+    B = 512
+    g = torch.Generator().manual_seed(1234)
+    maps = torch.rand(B, 3, 96, 96, generator=g).to(dev)
+    start = torch.zeros(B, 1, 12, 12, device=dev); start[:, :, 0, 0] = 1
+    goal = torch.zeros(B, 1, 12, 12, device=dev); goal[:, :, 11, 11] = 1
+    torch.manual_seed(1234)
+    na = NeuralAstar(encoder_input="rgb+", encoder_arch="CNNDownSize", encoder_depth=3, learn_obstacles=True,
+                     const=10.0).to(dev).eval()
+    fast = GraphedPlanner(na, maps, start, goal)
+    for _ in range(3):
+        fast.replay()
+    K = 20
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(K):
+        out = fast.replay()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / K
+    with torch.no_grad():
+        cost = na.encode(maps, start, goal)
+        ones = torch.ones_like(start)
+        for _ in range(3):
+            _native.forward(cost, start, goal, ones, 0.5, 144)
+        x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x.record()
+        for _ in range(10):
+            _native.forward(cost, start, goal, ones, 0.5, 144)
+        y.record()
+        torch.cuda.synchronize()
+    kus = x.elapsed_time(y) / 10 * 1e3
+    algo = 28 * 144 * B
+    ach = algo / (kus * 1e-6) / 1e9
+    return {"workload": "NeuralAstar inference, synthetic 96x96 RGB -> 12x12 (CNNDownSize d3, const 10, learn_obstacles), b=512",
+            "maps_per_s": B * 1e3 / ms, "ms_per_step": ms, "expansions_per_map": float(out.histories.sum()) / B,
+            "search_kernel_us": kus, "api": "GraphedPlanner replay (encoder + search in one CUDA graph)",
+            "roofline": {"bound": "hbm", "kernel": "astar_warp32_kernel<0,0,0>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "algorithmic_bytes_per_launch": algo}}
+
+
+def config_c5(dev, peak, rank, timer, dist, world):
+    """BASELINE.json configs[4]: synthetic 256x256 Moore grids, 1024 DISTINCT maps per GPU (seed 1234 + rank),
+    VanillaAstar semantics; sharded over the ranks with no data-path collective."""
+    from c5_data import c5_maps
+    from neural_astar import _native
+
+    Hh = Ww = 256
+    per_gpu = 1024
+    t0 = time.time()
+    obst, start, goal = c5_maps(per_gpu, Hh, Ww, 1234 + rank)
+    gen_s = time.time() - t0
+    o, s, g = (torch.from_numpy(x).to(dev) for x in (obst, start, goal))
+    fn = lambda: _native.forward(o, s, g, o, 0.5, Ww * Ww)  # noqa: E731
+    for _ in range(3):
+        out = fn()
+    reps = 3
+    ms, out = timer.loop(lambda: [fn() for _ in range(reps)][-1])
+    ms /= reps
+    ns = out[3].float()
+    stats = torch.tensor([ms, float(ns.sum()), float(ns.max()), float((out[2] >= 0).sum())], device=dev, dtype=torch.float64)
+    if dist is not None:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, exp_total, exp_max, solved = float(mx[0]), float(sm[1]), float(mx[2]), float(sm[3])
+    else:
+        ms, exp_total, exp_max, solved = (float(v) for v in stats)
+    maps_total = per_gpu * world
+    algo = 24 * Hh * Ww * per_gpu     # cost aliases obstacles: 24*N bytes per map (SURVEY 8(d))
+    ach = algo / (ms * 1e-3) / 1e9
+    return {"workload": f"VanillaAstar, synthetic 256x256 Moore grids (p_obst 0.2, Chebyshev(start,goal) >= 128), "
+                        f"{per_gpu} distinct maps per GPU x {world} GPU(s), seed 1234+rank",
+            "maps_per_s": maps_total / (ms * 1e-3), "maps_per_s_per_gpu": per_gpu / (ms * 1e-3), "ms_per_launch": ms,
+            "expansions_per_s": exp_total / (ms * 1e-3), "mean_expansions_per_map": exp_total / maps_total,
+            "max_expansions_per_map": exp_max, "solved": solved, "us_per_step_longest_map": ms * 1e3 / max(exp_max, 1.0),
+            "engine": "5 (binary-cost, CTA per map, nastar_bin16.cuh)" if _native.lib().nastar_b200_bin16_supported(Hh, Ww)
+                      and os.environ.get("NASTAR_B200_BIN16", "1") != "0" else "3 (generic, HBM workspace)",
+            "map_generation_s_per_rank": gen_s,
+            "roofline": {"bound": "hbm", "kernel": "astar_bin16_kernel<8>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "algorithmic_bytes_per_launch": algo, "per_gpu": True}}
+
+
+def bench_ours(args):
+    _paths(ours=True)
+    from neural_astar import _native
+    from neural_astar.planner import encoder as _enc
+    from neural_astar.utils.inference import PipelinedPlanner
 
     _native.lib()  # fail loudly when the CUDA engine is not built
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    pinned_cpus = pin_to_gpu_numa(local_rank)
     if world > 1:
         import torch.distributed as dist
 
@@ -251,143 +510,148 @@ def bench_ours(args):
     assert args.gpus == world, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    timer = Timer(dist, dev)
+    K, Wm = args.steps, max(args.warmup, 3)
 
     maps_np, start_np, goal_np, golden = load_problem()
     planner = load_planner(dev)
     maps, start, goal = (torch.from_numpy(x).to(dev) for x in (maps_np, start_np, goal_np))
-    # host-side pinned copies for the end-to-end leg
-    h_in = [torch.from_numpy(x).pin_memory() for x in (maps_np, start_np, goal_np)]
-    h_hist = torch.empty((BATCH, 1, H, W), dtype=torch.float32).pin_memory()
-    h_paths = torch.empty((BATCH, 1, H, W), dtype=torch.int64).pin_memory()
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    fast = None
-    if not args.no_graph:
-        from neural_astar.utils.inference import GraphedPlanner
+    # ---- the two timed legs: pipelined planner, device-resident ring / pinned host buffers -----------------------
+    ring_n = 112   # 112 x 1.2 MB of inputs = 138 MB > 126 MB L2: a step's inputs are never L2-resident
+    ring = torch.stack([torch.stack([t.roll(i, 0) for t in (maps, start, goal)]) for i in range(ring_n)])
+    pipe_dev = PipelinedPlanner(planner, maps, start, goal)
+    pipe_host = PipelinedPlanner(planner, maps, start, goal, host=True)
+    pipe_dev.prepare()
+    pipe_host.prepare()
+    step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
 
-        fast = GraphedPlanner(planner, maps, start, goal)   # public API: CUDA-graph replay of the same forward
+    def loop_dev(n, evs=None):
+        for k in range(n):
+            slot = ring[k % ring_n]
+            pipe_dev.submit(slot[0], slot[1], slot[2])
+            if evs is not None:
+                evs[k + 1].record()
+        return pipe_dev.drain()
 
-    def step():
-        with torch.no_grad():
-            return fast(maps, start, goal) if fast is not None else planner(maps, start, goal)
+    def loop_host(n):
+        for _ in range(n):
+            pipe_host.submit()
+        return pipe_host.drain()
 
-    def step_e2e():
-        with torch.no_grad():
-            if fast is not None:
-                for dst, src in zip(fast.static_inputs, h_in):      # pinned host -> the graph's input buffers
-                    dst.copy_(src, non_blocking=True)
-                out = fast.replay()
-            else:
-                out = planner(*[x.to(dev, non_blocking=True) for x in h_in])
-            h_hist.copy_(out.histories, non_blocking=True)
-            h_paths.copy_(out.paths, non_blocking=True)
-        return out
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def native_launches():
-        # host-side launches plus the library kernels re-issued by graph replays
-        return _native.launch_count() + (fast.replays * fast.native_launches_per_replay if fast is not None else 0)
-
-    def timed(fn, steps, all_ranks=True):
-        """all_ranks=False: a rank-local measurement (no collective may be issued by a subset of ranks)."""
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        l0 = native_launches()
-        barrier() if all_ranks else torch.cuda.synchronize()
-        out = None
-        for a, b in evs:
-            flush.zero_()  # evict the inputs from L2 between timed iterations (outside the event pair)
-            a.record()
-            out = fn()
-            b.record()
-        barrier() if all_ranks else torch.cuda.synchronize()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        return total_ms, out, native_launches() - l0
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-        step_e2e()
+    loop_dev(Wm)
+    loop_host(Wm)
     torch.cuda.synchronize()
 
     with ClockSampler(local_rank) as clk:
-        total_ms, out, launches = timed(step, args.steps)
-        e2e_ms, _, _ = timed(step_e2e, args.steps)
-    # search kernel alone (roofline numerator's denominator): precomputed cost maps, same stream
-    with torch.no_grad():
-        cost = planner.encode(maps, start, goal)
-    kern_ms, _, _ = timed(lambda: _native.forward(cost, start, goal, maps, 0.5, W * W), args.steps)
-    # the same kernel with the SMs filled: fixture tiled x1000 (100 000 maps, 2.87 GB of algorithmic traffic,
-    # larger than L2) — the figure that reflects kernel quality rather than the b=100 latency floor
-    sat = None
-    if rank == 0 and not args.no_saturated:
-        rep = 1000
-        big = [x.repeat(rep, 1, 1, 1) for x in (cost, start, goal, maps)]
-        sat_steps = 5
-        sat_fn = lambda: _native.forward(*big, 0.5, W * W)  # noqa: E731
-        for _ in range(3):   # warm-up: the 1.2 GB of outputs must come from the caching allocator, not cudaMalloc
-            sat_out = sat_fn()
-        del sat_out
-        sat_ms, sat_out, _ = timed(sat_fn, sat_steps, all_ranks=False)
-        sat_s = sat_ms * 1e-3 / sat_steps
-        sat = {"batch": BATCH * rep, "kernel_ms": sat_s * 1e3, "maps_per_s": BATCH * rep / sat_s,
-               "expansions_per_s": float(sat_out[0].sum()) / sat_s,
-               "achieved": ALGO_BYTES_PER_MAP * BATCH * rep / sat_s / 1e9, "unit": "GB/s"}
-        del big, sat_out
+        l0 = pipe_dev.native_launches
 
-    expansions = float(out.histories.sum())
-    # parity spot-check against the committed reference output for these inputs (learned costs differ
-    # in the last ulp between cuDNN and the CPU encoder, so compare the vanilla search exactly)
+        def body():
+            step_evs[0].record()
+            return loop_dev(K, step_evs)
+
+        total_ms, out = timer.loop(body)
+        launches = pipe_dev.native_launches - l0
+        step_ms = [step_evs[i].elapsed_time(step_evs[i + 1]) for i in range(K)]
+        e2e_ms, _ = timer.loop(lambda: loop_host(K))
+        torch.cuda.synchronize()
+        expansions = float(out.histories.sum())     # last batch (a rotation of the same 100 maps)
+        # search kernel alone (roofline denominator): finished cost maps, same stream, L2 flushed between launches
+        with torch.no_grad():
+            cost = planner.encode(maps, start, goal)
+        kern_ts, _ = timer.per_step(lambda: _native.forward(cost, start, goal, maps, 0.5, W * W), K, flush)
+        kern_ms = float(np.sum(kern_ts))
+        # the same kernel with the SMs filled: the 1000 distinct maps of mazes_032 (train+valid+test) x100 =
+        # 100 000 maps, 2.87 GB of algorithmic traffic (larger than L2)
+        sat = None
+        if rank == 0 and not args.no_saturated:
+            o1k, s1k, g1k, _ = load_problem("inputs_mazes032_all1000")
+            o1k, s1k, g1k = (torch.from_numpy(x).to(dev) for x in (o1k, s1k, g1k))
+            with torch.no_grad():
+                c1k = torch.cat([planner.encode(o1k[i:i + 200], s1k[i:i + 200], g1k[i:i + 200]) for i in range(0, 1000, 200)])
+            rep = 100
+            big = [x.repeat(rep, 1, 1, 1) for x in (c1k, s1k, g1k, o1k)]
+            sat_fn = lambda: _native.forward(*big, 0.5, W * W)  # noqa: E731
+            for _ in range(3):   # warm-up: the 1.2 GB of outputs must come from the caching allocator, not cudaMalloc
+                sat_out = sat_fn()
+            del sat_out
+            sat_ts, sat_out = timer.per_step(sat_fn, 5, flush)
+            sat_s = float(np.mean(sat_ts)) * 1e-3
+            nb = 1000 * rep
+            sat = {"batch": nb, "distinct_maps": 1000, "kernel_ms": sat_s * 1e3, "maps_per_s": nb / sat_s,
+                   "expansions_per_s": float(sat_out[0].sum()) / sat_s,
+                   "achieved": ALGO_BYTES_PER_MAP * nb / sat_s / 1e9, "unit": "GB/s"}
+            del big, sat_out
+        peak, peak_src = peak_hbm()
+        configs = {}
+        if not args.no_configs:
+            if rank == 0 and world == 1:
+                configs["c3"] = config_c3(dev, peak)
+                configs["c4"] = config_c4(dev, peak)
+            c5 = config_c5(dev, peak, rank, timer, dist, world)
+            if rank == 0:
+                configs["c5"] = c5
+
+    # parity spot-check against the committed reference output for these inputs (learned costs differ in the last
+    # ulp between cuDNN and the CPU encoder, so compare the vanilla search exactly)
     van = _native.forward(maps, start, goal, maps, 0.5, W * W)
     assert np.array_equal(van[0].cpu().numpy() != 0, golden.bits("hist_bits") != 0), "search parity lost"
 
     if dist is not None:
-        t = torch.tensor([total_ms, e2e_ms, kern_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_ms, kern_ms, max(step_ms)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, kern_ms = (float(x) for x in t)
+        total_ms, e2e_ms, kern_ms, step_max = (float(x) for x in t)
         e = torch.tensor([expansions, float(launches)], device=dev, dtype=torch.float64)
         dist.all_reduce(e, op=dist.ReduceOp.SUM)
         expansions, launches = float(e[0]), int(e[1])
+    else:
+        step_max = max(step_ms)
     if rank == 0:
-        maps_total = BATCH * world * args.steps
+        maps_total = BATCH * world * K
         value = maps_total / (total_ms * 1e-3)
-        peak, peak_src = peak_hbm()
-        kern_s = kern_ms * 1e-3 / args.steps
+        kern_s = kern_ms * 1e-3 / K
         achieved = ALGO_BYTES_PER_MAP * BATCH / kern_s / 1e9
+        h2d = int(sum(x.numel() * x.element_size() for x in pipe_host.host_inputs[0]))
+        d2h = int(sum(x.numel() * x.element_size() for x in pipe_host.host_outputs[0]))
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "mazes_032_moore_c8 test split (100 maps, seed-1234 starts) + shipped checkpoint, committed fixtures",
-            "config": {"workload": "NeuralAstar inference, mazes_032_moore_c8 32x32, batch=100 (BASELINE.json configs[1])",
-                       "batch_per_gpu": BATCH, "grid": "32x32", "g_ratio": 0.5, "T_max": W * W,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 search (bit-exact masks) / " + ("tf32" if _enc.ALLOW_TF32 else "fp32")
+                     + " encoder 3x3 convs (cuDNN tensor cores, torch's default), fp32 head",
+            "data": DATA,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "grid": "32x32", "g_ratio": 0.5, "T_max": W * W,
                        "parallelism": f"dp{world} (independent map shards, no data-path collective)",
-                       "api": ("neural_astar.utils.inference.GraphedPlanner (CUDA-graph replay of planner.forward; inputs "
-                               "copied into static buffers, outputs cloned)" if fast is not None else "planner(...) eager"),
-                       "l2": "512 MiB buffer rewritten between timed iterations (L2 flushed)",
-                       "timing": "CUDA events per step on the launching stream, sum over steps, max over ranks"},
-            "expansions_per_s": expansions * (args.steps if dist is None else args.steps) / (total_ms * 1e-3),
+                       "api": "neural_astar.utils.inference.PipelinedPlanner (one CUDA-graph launch per step: search of "
+                              "batch k || encoder of batch k+1)",
+                       "l2": f"inputs rotate through a ring of {ring_n} device-resident batches (138 MB > 126 MB L2)",
+                       "timing": "CUDA events around the whole K-step loop (pipeline fill + drain inside), barrier + "
+                                 "synchronize both sides, max over ranks",
+                       "rank_cpu_affinity": pinned_cpus},
+            "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": step_max,
+            "expansions_per_s": expansions * K / (total_ms * 1e-3),
             "search_kernel_us": kern_s * 1e6,
-            "e2e": {"value": maps_total / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(sum(x.numel() * x.element_size() for x in h_in)),
-                    "d2h_bytes_per_step": int(h_hist.numel() * 4 + h_paths.numel() * 8)},
+            "e2e": {"value": maps_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K,
+                    "api": "PipelinedPlanner(host=True): pinned H2D of the batch and D2H of histories+paths inside each step's graph"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "nastar::astar_warp32_kernel<false,false>",
+            "roofline": {"bound": "hbm", "kernel": "nastar::astar_warp32_kernel<0,0,0>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": ncu_traffic(),
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_MAP * BATCH,
-                         "note": "b=100 occupies 100 of 148 SMs with one warp each: latency-bound by the "
-                                 "longest map's dependent steps; `saturated` is the same kernel at b=100000"},
+                         "note": "b=100 occupies 100 of 148 SMs with one warp each: latency-bound by the longest map's "
+                                 "dependent steps; `saturated` is the same kernel at b=100000 (1000 distinct maps x100)"},
             "clocks": clk.summary(),
         }
         if sat is not None:
             sat["peak"] = peak
             sat["frac"] = sat["achieved"] / peak
             line["roofline"]["saturated"] = sat
+        if configs:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = run_cpu_baseline(maps_np, start_np, goal_np)
+            line["cpu_baseline"] = run_cpu_baseline()
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -402,7 +666,9 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-saturated", action="store_true", help="skip the b=100000 kernel-only measurement")
-    ap.add_argument("--no-graph", action="store_true", help="time the eager planner(...) call instead of GraphedPlanner")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs block (training / WarCraft / 256x256)")
+    ap.add_argument("--port", action="store_true", help="--impl reference: use the C restatement even if the reference is staged")
+    ap.add_argument("--budget", type=float, default=150.0, help="--impl reference: seconds for warm-up + timed steps")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

@@ -174,6 +174,11 @@ int nastar_b200_pack_inputs(const float *map_designs, int32_t C, int32_t Hm, int
 int nastar_b200_cost_from_taps(const float *taps, int32_t B, int32_t H, int32_t W, float bias, float scale,
                                float *cost, void *stream);
 
+/* Self-test of engine 5's branch-free square root: counts, on the device, the integers i in [0, n) for which it
+ * differs in any bit from the IEEE-rounded sqrtf(i) that get_heuristic needs (differentiable_astar.py:47-50).
+ * `mismatches` is a device int the caller zeroed.  n = 2*511*511+1 covers every argument a 512-row map can produce. */
+int nastar_b200_selftest_sqrt(int32_t n, int32_t *mismatches, void *stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t nastar_b200_launch_count(void);
 

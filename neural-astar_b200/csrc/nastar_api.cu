@@ -404,6 +404,15 @@ int nastar_b200_cost_from_taps(const float* taps, int32_t B, int32_t H, int32_t 
     return NASTAR_OK;
 }
 
+int nastar_b200_selftest_sqrt(int32_t n, int32_t* mismatches, void* stream_v) {
+    if (n <= 0 || !mismatches) return NASTAR_EINVAL;
+    nastar::sqrt_rn_int_check_kernel<<<num_sms() * 4, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(n, mismatches);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
+}
+
 uint64_t nastar_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* nastar_b200_status_string(int s) {

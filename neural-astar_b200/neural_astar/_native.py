@@ -72,6 +72,7 @@ EXPORTS = (
     "nastar_b200_bin16_supported",
     "nastar_b200_pack_inputs",
     "nastar_b200_cost_from_taps",
+    "nastar_b200_selftest_sqrt",
     "nastar_b200_launch_count",
     "nastar_b200_status_string",
     "nastar_b200_last_cuda_error",
@@ -121,6 +122,8 @@ def lib():
     L.nastar_b200_cost_from_taps.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                              ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
     L.nastar_b200_cost_from_taps.restype = ctypes.c_int
+    L.nastar_b200_selftest_sqrt.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    L.nastar_b200_selftest_sqrt.restype = ctypes.c_int
     L.nastar_b200_launch_count.restype = ctypes.c_uint64
     L.nastar_b200_status_string.argtypes = [ctypes.c_int]
     L.nastar_b200_status_string.restype = ctypes.c_char_p

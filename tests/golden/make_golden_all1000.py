@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""All 1000 problems of mazes_032_moore_c8 (800 train + 100 valid + 100 test) as ONE small input fixture for the
+saturated-throughput measurement of bench.py ("tile the 1000 available maps ... to fill the GPU").
+Inputs only (bit-packed maps, start / goal indices); start positions from the reference's MazeDataset
+(/root/reference/src/neural_astar/utils/data.py:152-221) under np.random.seed(1234).
+
+    python tests/golden/make_golden_all1000.py     # build container only (needs /root/reference)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg  # noqa: E402
+import torch  # noqa: E402
+
+
+def main():
+    np.random.seed(1234)
+    torch.manual_seed(1234)
+    maps, starts, goals = [], [], []
+    for split in ("train", "valid", "test"):
+        ds = mg.MazeDataset(f"{mg.MPD}/mazes_032_moore_c8.npz", split)
+        for i in range(len(ds)):
+            m, s, g, _ = ds[i]
+            maps.append(m); starts.append(s[:1]); goals.append(g)
+    maps, starts, goals = (np.stack(x) for x in (maps, starts, goals))
+    mg.save("inputs_mazes032_all1000", dict(desc="mazes_032_moore_c8 train+valid+test (1000 maps), seed-1234 starts; inputs only"),
+            shape=np.array([len(maps), 32, 32], np.int32), obst_bits=mg.pack(maps[:, 0]),
+            start_idx=mg.onehot_idx(starts), goal_idx=mg.onehot_idx(goals))
+
+
+if __name__ == "__main__":
+    main()

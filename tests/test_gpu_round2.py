@@ -74,6 +74,17 @@ def test_bin16_engine_vs_oracle(native, oracle, H, W, B):
     np.testing.assert_array_equal(plen.cpu().numpy(), ref.paths.sum((1, 2, 3)))
 
 
+def test_bin16_sqrt_is_ieee_for_every_reachable_argument(native):
+    """Engine 5 evaluates get_heuristic's sqrt with a branch-free sequence; it must equal the IEEE-rounded sqrtf for
+    every integer dy^2 + dx^2 a map of up to 512 rows / 1024 columns can produce."""
+    import ctypes
+
+    n = 511 * 511 + 1023 * 1023 + 1
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = native.lib().nastar_b200_selftest_sqrt(n, bad.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st == 0 and int(bad.item()) == 0
+
+
 def test_bin16_edge_cases_and_redo(native, oracle):
     """Unreachable goal, start == goal, start on an obstacle cell, g_ratio != 0.5, a step cap, and a batch in which
     some maps carry non-binary costs (those are re-run by the generic engine inside the same call)."""
@@ -125,6 +136,7 @@ def test_pair_launch_equals_two_calls(native, H, W):
     obst, start, goal = _corner_problem(rng, B, H, W)
     cost = (obst * (0.2 + rng.rand(B, 1, H, W))).astype(np.float32)
     c, s, g, o = _cu(cost), _cu(start), _cu(goal), _cu(obst)
+    native.forward(c, s, g, o, 0.5, W * W)      # one-time table fill of the warp engines is a launch of its own
     before = native.launch_count()
     hist, paths, ts, ns, _, (ncl, plen) = native.forward(c, s, g, o, 0.5, W * W, pair=True, want_counts=True)
     n_launch = native.launch_count() - before
