@@ -15,6 +15,8 @@ checkpoint's encoder output (const = 1) and (c) the same x10 (const = 10, tighte
 Reported per (dataset, cost kind): maps, selections, maps whose histories / paths masks differ, differing trace
 positions, and maps whose traces differ at all.
 """
+import contextlib
+import io
 import os
 import sys
 import time
@@ -49,7 +51,8 @@ def batches(path):
     torch.manual_seed(1234)
     out = []
     for split in ("train", "valid", "test"):
-        ds = MazeDataset(path, split)
+        with contextlib.redirect_stdout(io.StringIO()):    # the dataset announces its size like the reference does
+            ds = MazeDataset(path, split)
         n = len(ds)
         items = [ds[i] for i in range(n)]
         out.append(tuple(np.stack([it[k] for it in items]).astype(np.float32) for k in range(3)))
