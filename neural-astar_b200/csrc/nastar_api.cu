@@ -197,12 +197,14 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         nastar::W32Args a{};
         a.f = *p;
         const bool noexit = (p->flags & NASTAR_FWD_NO_EARLY_EXIT) != 0;
-        if (p->trace) {
-            if (noexit) nastar::astar_warp32_kernel<true, false, true><<<nmaps, 32, 0, stream>>>(a);
-            else nastar::astar_warp32_kernel<true, false, false><<<nmaps, 32, 0, stream>>>(a);
+        const bool fused = (p->cost_kind != NASTAR_COST_PLANE);
+        auto go = [&](auto kernel) { kernel<<<nmaps, 32, 0, stream>>>(a); };
+        if (fused) {
+            if (p->trace) { if (noexit) go(nastar::astar_warp32_kernel<true, false, true, true>); else go(nastar::astar_warp32_kernel<true, false, false, true>); }
+            else          { if (noexit) go(nastar::astar_warp32_kernel<false, false, true, true>); else go(nastar::astar_warp32_kernel<false, false, false, true>); }
         } else {
-            if (noexit) nastar::astar_warp32_kernel<false, false, true><<<nmaps, 32, 0, stream>>>(a);
-            else nastar::astar_warp32_kernel<false, false, false><<<nmaps, 32, 0, stream>>>(a);
+            if (p->trace) { if (noexit) go(nastar::astar_warp32_kernel<true, false, true>); else go(nastar::astar_warp32_kernel<true, false, false>); }
+            else          { if (noexit) go(nastar::astar_warp32_kernel<false, false, true>); else go(nastar::astar_warp32_kernel<false, false, false>); }
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (engine == 4) {

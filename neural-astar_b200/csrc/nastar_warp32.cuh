@@ -67,7 +67,9 @@ struct __align__(16) W32Smem {
 };
 
 // kNoExit (forward only): NASTAR_FWD_NO_EARLY_EXIT — keep stepping after the solve step, exactly T steps.
-template <bool kTrace, bool kBwd, bool kNoExit = false>
+// kFused (forward only): the prologue may have to finish the encoder (NASTAR_COST_LOGIT / NASTAR_COST_TAPS); kept out
+// of the plain instantiation so that its cold instruction footprint stays small.
+template <bool kTrace, bool kBwd, bool kNoExit = false, bool kFused = false>
 __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     constexpr bool kContinue = kBwd || kNoExit;   // the loop does not stop at the solve step
     __shared__ W32Smem S;
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     const float* gGoal = p.goal + int64_t(bi) * p.goal_stride;
     const float* gObst = p.obst + int64_t(bi) * p.obst_stride;
     const float* gCost = vanilla_half ? gObst : (p.cost + int64_t(bi) * p.cost_stride);
-    const int cost_kind = (kBwd || vanilla_half) ? NASTAR_COST_PLANE : p.cost_kind;
+    const int cost_kind = (!kFused || kBwd || vanilla_half) ? NASTAR_COST_PLANE : p.cost_kind;
     const bool cost_plane = (cost_kind == NASTAR_COST_PLANE);
     const bool obst_is_cost = cost_plane && (gObst == gCost);
 
@@ -111,10 +113,10 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
             if (!obst_is_cost) tma_load_1d(tObst, gObst, bytes, bar);
         }
         __syncwarp();
-        if (!cost_plane) {
+        if (kFused && !cost_plane) {
             // fused encoder hand-off: the cost plane is produced here from the encoder's raw
             // output while the TMA copies of the other planes are in flight
-#pragma unroll 4
+#pragma unroll 1
             for (int y = 0; y < H; ++y)
                 S.cost[(y << 5) + lane] = cost_value(cost_kind, gCost, y, lane, H, W, p.cost_bias, p.cost_scale);
         }
@@ -141,7 +143,8 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
             for (int u = 0; u < kRows; ++u) {
                 const bool ok = in && (y0 + u < H);
                 const int i = (y0 + u) * W + lane;
-                vc[u] = ok ? cost_value(cost_kind, gCost, y0 + u, lane, H, W, p.cost_bias, p.cost_scale) : 0.f;
+                vc[u] = ok ? (kFused ? cost_value(cost_kind, gCost, y0 + u, lane, H, W, p.cost_bias, p.cost_scale)
+                                     : __ldg(gCost + i)) : 0.f;
                 vo[u] = obst_is_cost ? vc[u] : (ok ? __ldg(gObst + i) : 0.f);
                 vs[u] = ok ? __ldg(gStart + i) : 0.f;
                 vg[u] = ok ? __ldg(gGoal + i) : 0.f;
