@@ -31,8 +31,9 @@ struct GenericLayout {
     __host__ __device__ size_t smem_planes() const { return size_t(npad()) * 13; }
     // per-CTA workspace slot of the kGlobal variant: g, f (fp32) + parent (u8)
     __host__ __device__ size_t slot_bytes() const { return (size_t(npad()) * 9 + 255) & ~size_t(255); }
-    // backward adds a fp32 plane (v) and a fp64 plane (acc) per slot, always in the workspace
-    __host__ __device__ size_t bwd_bytes() const { return (size_t(npad()) * 12 + 255) & ~size_t(255); }
+    // backward adds per slot, always in the workspace: acc (fp64), A0 and B0 (fp64: prefix sums at the start of the
+    // cell's current open interval) and v (fp32) — 28 B per cell
+    __host__ __device__ size_t bwd_bytes() const { return (size_t(npad()) * 28 + 255) & ~size_t(255); }
     __host__ __device__ size_t slot_total(bool global_state, bool bwd) const {
         return (global_state ? slot_bytes() : 0) + (bwd ? bwd_bytes() : 0);
     }
@@ -58,9 +59,13 @@ __device__ __forceinline__ float gen_warp_sum(float v) {
     return v;
 }
 
-// kBwd = true replays the search for *T_batch steps and accumulates the closed-form gradient
-//  with a dense softmax pass per step over two fp32 planes (v, acc) kept in the
-// per-CTA workspace slot (L2 resident).  Functional, not yet tuned: O(N/32) per step.
+// kBwd = true replays the search for *T_batch steps and accumulates the closed-form gradient (SURVEY App. B)
+//   dL/dcost[p] = -(1-g_ratio)/sqrt(W) * sum_t y_t[p] * (Gh[p] - <Gh, y_t>),   y_t = v_t / S_t over the open set,
+// EVENT-BASED: v_t[p] = exp(-f_t[p]/sqrt(W)) only changes when p is opened, relaxed or closed, so a cell's
+// contribution over an interval [t0, t1) of constant v is v * (Gh[p] * (A(t1)-A(t0)) - (B(t1)-B(t0))) with the
+// prefix sums A(t) = sum_{tau<t} 1/S_tau, B(t) = sum_{tau<t} D_tau/S_tau^2, D_t = <Gh, v_t>.  S and D are
+// maintained incrementally in fp64 from the <= 9 events of a step — O(1) work per step instead of a dense
+// O(N/32) softmax pass (round 1).  Per-cell state (v, A(t0), B(t0), acc) lives in the per-CTA workspace slot.
 // kNoExit (forward only): NASTAR_FWD_NO_EARLY_EXIT — keep stepping after the solve step, exactly T steps.
 template <bool kGlobal, bool kTrace, bool kBwd, bool kNoExit = false>
 __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
@@ -90,12 +95,16 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         Par = reinterpret_cast<uint8_t*>(F + np);
     }
     float* V = nullptr;     // backward: v = exp(-f/sqrt(W)) of open cells, else 0
-    double* ACC = nullptr;  // backward: sum_t y_t[p] * (Gh[p] - <Gh, y_t>), fp64 (thousands of steps on big maps)
+    double* ACC = nullptr;  // backward: sum over closed intervals of v * (Gh * dA - dB)
+    double* A0 = nullptr;   // backward: A(t0), B(t0) of the cell's current interval
+    double* B0 = nullptr;
     if (kBwd) {
         unsigned char* slot = static_cast<unsigned char*>(p.workspace) + size_t(blockIdx.x) * L.slot_total(kGlobal, true) +
                               (kGlobal ? L.slot_bytes() : 0);
         ACC = reinterpret_cast<double*>(slot);
-        V = reinterpret_cast<float*>(ACC + np);
+        A0 = ACC + np;
+        B0 = A0 + np;
+        V = reinterpret_cast<float*>(B0 + np);
     }
     uint32_t* sPass = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
     uint32_t* sOpen = reinterpret_cast<uint32_t*>(sp); sp += size_t(L.nbits) * 4;
@@ -225,18 +234,26 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             for (int i = lane; i < N; i += 32) { V[i] = 0.f; ACC[i] = 0.0; }
             __syncwarp();
         }
+        // backward running sums (replicated in every lane): S = sum of v over the open set, D = <Gh, v>,
+        // A / B = prefix sums of 1/S and D/S^2 over the steps executed so far
+        double Ssum = 0.0, Dsum = 0.0, Acum = 0.0, Bcum = 0.0;
+        auto gh_at = [&](int i) -> float { return (blocked && i == goal_idx) ? 0.f : __ldg(gG + i); };
         if (start_idx >= 0 && lane == 0) {
             const int sy = start_idx / W, sx = start_idx - sy * W;
             const float h0 = __fadd_rn(heuristic(sy, sx, gy, gx), cost_at(start_idx));
             const float f0 = f_value(gr, omg, 0.f, h0);
             G[start_idx] = 0.f;
             F[start_idx] = f0;
-            if (kBwd) V[start_idx] = expf(__fdiv_rn(-f0, a.sqrt_w));
+            if (kBwd) { V[start_idx] = expf(__fdiv_rn(-f0, a.sqrt_w)); A0[start_idx] = 0.0; B0[start_idx] = 0.0; }
             sOpen[sy * Wd + (sx >> 5)] = 1u << (sx & 31);
             sRmKey[sy] = fkey(f0);
             sRmCol[sy] = sx;
         }
         __syncwarp();
+        if (kBwd && start_idx >= 0) {
+            Ssum = double(V[start_idx]);
+            Dsum = double(gh_at(start_idx)) * Ssum;
+        }
         uint32_t bk = kKeyInf;
         int by = 0;
         for (int y = lane; y < H; y += 32) {
@@ -251,32 +268,20 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         for (int t = 0; t < T; ++t) {
             const uint32_t m = __reduce_min_sync(kFull, bk);
             if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
+            double A1 = 0.0, B1 = 0.0;   // prefix sums INCLUDING step t (events of step t take effect from t+1 on)
             if (kBwd) {
-                double s_ = 0.0, d_ = 0.0;
-                for (int i = lane; i < N; i += 32) {
-                    const float v = V[i];
-                    if (v != 0.f) {
-                        const float g = (blocked && i == goal_idx) ? 0.f : __ldg(gG + i);
-                        s_ += double(v);
-                        d_ += double(g) * double(v);
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    s_ += __shfl_xor_sync(kFull, s_, o);
-                    d_ += __shfl_xor_sync(kFull, d_, o);
-                }
+                const double inv = 1.0 / Ssum;
+                const double a_t = inv, b_t = Dsum * inv * inv;
                 const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
-                const double inv = (last ? double(Tb - t) : 1.0) / s_;
-                const double dd = d_ / s_;
-                for (int i = lane; i < N; i += 32) {
-                    const float v = V[i];
-                    if (v != 0.f) {
-                        const float g = (blocked && i == goal_idx) ? 0.f : __ldg(gG + i);
-                        ACC[i] += double(v) * inv * (double(g) - dd);
-                    }
+                if (last) {
+                    // the map is solved and re-selects its goal with a frozen open set until step T_batch-1
+                    // (SURVEY App. A.4): the remaining Tb - t steps advance the prefix sums linearly
+                    Acum += double(Tb - t) * a_t;
+                    Bcum += double(Tb - t) * b_t;
+                    break;
                 }
-                if (last) break;
+                A1 = Acum + a_t;
+                B1 = Bcum + b_t;
             }
             const int r = int(__reduce_min_sync(kFull, (bk == m) ? uint32_t(by) : 0x7FFFFFFFu));
             const int c = sRmCol[r];
@@ -286,10 +291,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             const bool solved = (ind == goal_idx);
             if (lane == 0) {
                 sClosed[r * Wd + (c >> 5)] |= 1u << (c & 31);
-                if (!solved) {
-                    sOpen[r * Wd + (c >> 5)] &= ~(1u << (c & 31));
-                    if (kBwd) V[ind] = 0.f;
-                }
+                if (!solved) sOpen[r * Wd + (c >> 5)] &= ~(1u << (c & 31));
             }
             __syncwarp();
             // rescan of row r over its remaining, pre-expansion open cells (ascending x => first min)
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             __syncwarp();  // every read of the pre-expansion open bits is done
             const bool upd = valid && passable && (isopen ? (gn > g2) : !isclosed);
             uint32_t key = kKeyInf;
+            double dS = 0.0, dD = 0.0;   // backward: this lane's change of S and D
             if (upd) {
                 const float hn = __fadd_rn(heuristic(y, x, gy, gx), cost_at(n));
                 const float fn = f_value(gr, omg, g2, hn);
@@ -329,7 +332,39 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
                 Par[n] = uint8_t(k9);
                 atomicOr(&sOpen[y * Wd + (x >> 5)], 1u << (x & 31));
                 key = fkey(fn);
-                if (kBwd) V[n] = expf(__fdiv_rn(-fn, a.sqrt_w));
+                if (kBwd) {
+                    // event: the cell's softmax weight changes from v_old (0 if it was not open) to v_new after this step
+                    const float v_old = V[n], v_new = expf(__fdiv_rn(-fn, a.sqrt_w));
+                    const double gh = double(gh_at(n));
+                    if (v_old != 0.f) ACC[n] += double(v_old) * (gh * (A1 - A0[n]) - (B1 - B0[n]));
+                    V[n] = v_new;
+                    A0[n] = A1;
+                    B0[n] = B1;
+                    dS = double(v_new) - double(v_old);
+                    dD = gh * dS;
+                }
+            }
+            if (kBwd) {
+                if (lane == 9 && !solved) {
+                    // event: the selected cell leaves the open set (the goal stays open, :224)
+                    const float v_old = V[ind];
+                    const double gh = double(gh_at(ind));
+                    ACC[ind] += double(v_old) * (gh * (A1 - A0[ind]) - (B1 - B0[ind]));
+                    V[ind] = 0.f;
+                    dS = -double(v_old);
+                    dD = gh * dS;
+                }
+#pragma unroll
+                for (int o = 8; o; o >>= 1) {          // events sit on lanes 0..9
+                    dS += __shfl_xor_sync(kFull, dS, o);
+                    dD += __shfl_xor_sync(kFull, dD, o);
+                }
+                dS = __shfl_sync(kFull, dS, 0);
+                dD = __shfl_sync(kFull, dD, 0);
+                Ssum += dS;
+                Dsum += dD;
+                Acum = A1;
+                Bcum = B1;
             }
             if (solved && t_solve < 0) t_solve = t;
             if (!kContinue && solved) break;
@@ -366,9 +401,15 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         __syncwarp();
 
         if (kBwd) {
+            // close the intervals of the cells still open at the end, then scale
             const float coef = -omg / a.sqrt_w;
             float* gOut = a.grad_cost + int64_t(b) * N;
-            for (int i = lane; i < N; i += 32) gOut[i] = float(double(coef) * ACC[i]);
+            for (int i = lane; i < N; i += 32) {
+                double acc = ACC[i];
+                const float v = V[i];
+                if (v != 0.f) acc += double(v) * (double(gh_at(i)) * (Acum - A0[i]) - (Bcum - B0[i]));
+                gOut[i] = float(double(coef) * acc);
+            }
             __syncwarp();
         }
         if (!kBwd) {
