@@ -174,6 +174,13 @@ int nastar_b200_pack_inputs(const float *map_designs, int32_t C, int32_t Hm, int
 int nastar_b200_cost_from_taps(const float *taps, int32_t B, int32_t H, int32_t W, float bias, float scale,
                                float *cost, void *stream);
 
+/* Head of the encoder (its last 3x3 conv has ONE output channel, encoder.py:60-78): taps[p][k] = sum_c x[p][c] *
+ * w[c][k] for every pixel p of the channels-last activation x (fp32 [P][C], C in {32,64,128,256}), k = ky*3+kx.
+ * `w` is a HOST pointer to C*9 floats ([c][k], BatchNorm folded): it is passed to the kernel by value (constant
+ * bank), so it may change between calls without any device copy.  The 9-tap spatial gather + bias + sigmoid * const
+ * that finish the layer happen in nastar_b200_forward's NASTAR_COST_TAPS prologue (or nastar_b200_cost_from_taps). */
+int nastar_b200_head_taps(const float *x, int64_t P, int32_t C, const float *w_host, float *taps, void *stream);
+
 /* Self-test of engine 5's branch-free square root: counts, on the device, the integers i in [0, n) for which it
  * differs in any bit from the IEEE-rounded sqrtf(i) that get_heuristic needs (differentiable_astar.py:47-50).
  * `mismatches` is a device int the caller zeroed.  n = 2*511*511+1 covers every argument a 512-row map can produce. */

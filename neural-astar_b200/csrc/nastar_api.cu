@@ -130,6 +130,17 @@ __global__ void batch_steps_kernel(const int32_t* __restrict__ t_solve, const in
 }
 }  // namespace
 
+namespace {
+template <int C>
+cudaError_t launch_head(const float* x, int64_t P, const float* w_host, float* taps, cudaStream_t stream) {
+    nastar::HeadWeights<C> hw;
+    for (int i = 0; i < C * 9; ++i) hw.w[i] = w_host[i];
+    const int64_t blocks = (P + 127) / 128;
+    nastar::head_taps_kernel<C><<<unsigned(blocks), 128, 0, stream>>>(x, P, hw, taps);
+    return cudaGetLastError();
+}
+}  // namespace
+
 extern "C" {
 
 int nastar_b200_abi_version(void) { return NASTAR_B200_ABI_VERSION; }
@@ -403,6 +414,23 @@ int nastar_b200_cost_from_taps(const float* taps, int32_t B, int32_t H, int32_t 
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
+}
+
+int nastar_b200_head_taps(const float* x, int64_t P, int32_t C, const float* w_host, float* taps, void* stream_v) {
+    if (!x || !w_host || !taps || P <= 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return NASTAR_EINVAL;
+    if (P > (int64_t(1) << 31) * 127) return NASTAR_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    cudaError_t e;
+    switch (C) {
+        case 32: e = launch_head<32>(x, P, w_host, taps, stream); break;
+        case 64: e = launch_head<64>(x, P, w_host, taps, stream); break;
+        case 128: e = launch_head<128>(x, P, w_host, taps, stream); break;
+        case 256: e = launch_head<256>(x, P, w_host, taps, stream); break;
+        default: return NASTAR_EUNSUPPORTED;
+    }
+    if (e != cudaSuccess) return cuda_fail(e);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return NASTAR_OK;
 }
 

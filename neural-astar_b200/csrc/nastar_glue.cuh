@@ -55,4 +55,43 @@ __global__ void __launch_bounds__(256) cost_from_taps_kernel(const float* __rest
     }
 }
 
+// ---- single-output-channel head of the encoder: per-pixel partial products ---------------------------------------
+// The encoder's last layer is a 3x3 conv with ONE output channel (encoder.py:60-78, channels [...,256,1]).  Round 1
+// already evaluated it as a per-pixel [C] x [C,9] product followed by a 9-tap gather (planner/encoder.py
+// `_conv3x3_single_output`); the gather now lives in the search kernel's prologue (NASTAR_COST_TAPS).  The product
+// itself is 0.5 GFLOP over a 105 MB activation (b=100, 32x32, C=256): HBM-bound, and cuBLAS' skinny SGEMM reaches only
+// 1.2 TB/s on it (86 us).  Here: one thread per pixel streams its C contiguous channels with 128-bit loads and keeps
+// the 9 sums in registers; the C*9 weights arrive as a by-value kernel parameter, i.e. in the constant bank, so every
+// FFMA takes its weight operand straight from c[0x0][..] — no shared memory, no weight loads at all.
+template <int C>
+struct HeadWeights {
+    float w[C * 9];   // [c][k], k = ky*3+kx, BatchNorm already folded
+};
+
+template <int C>
+__global__ void __launch_bounds__(128) head_taps_kernel(const float* __restrict__ x, int64_t P,
+                                                        const __grid_constant__ HeadWeights<C> hw,
+                                                        float* __restrict__ out) {
+    const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const float4* xp = reinterpret_cast<const float4*>(x + p * C);
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+        const float4 v = __ldg(xp + c4);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            acc[k] = fmaf(v.x, hw.w[(4 * c4 + 0) * 9 + k], acc[k]);
+            acc[k] = fmaf(v.y, hw.w[(4 * c4 + 1) * 9 + k], acc[k]);
+            acc[k] = fmaf(v.z, hw.w[(4 * c4 + 2) * 9 + k], acc[k]);
+            acc[k] = fmaf(v.w, hw.w[(4 * c4 + 3) * 9 + k], acc[k]);
+        }
+    }
+    float* o = out + p * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = acc[k];
+}
+
 }  // namespace nastar

@@ -72,6 +72,7 @@ EXPORTS = (
     "nastar_b200_bin16_supported",
     "nastar_b200_pack_inputs",
     "nastar_b200_cost_from_taps",
+    "nastar_b200_head_taps",
     "nastar_b200_selftest_sqrt",
     "nastar_b200_launch_count",
     "nastar_b200_status_string",
@@ -122,6 +123,9 @@ def lib():
     L.nastar_b200_cost_from_taps.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                              ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
     L.nastar_b200_cost_from_taps.restype = ctypes.c_int
+    L.nastar_b200_head_taps.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]
+    L.nastar_b200_head_taps.restype = ctypes.c_int
     L.nastar_b200_selftest_sqrt.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     L.nastar_b200_selftest_sqrt.restype = ctypes.c_int
     L.nastar_b200_launch_count.restype = ctypes.c_uint64
@@ -267,6 +271,29 @@ def pack_inputs(map_designs: torch.Tensor, start: torch.Tensor, goal: torch.Tens
                                          ctypes.c_void_p(stream)), "nastar_b200_pack_inputs")
     del ks, kg
     return out.permute(0, 3, 1, 2)   # logical NCHW view with channels-last strides
+
+
+HEAD_CHANNELS = (32, 64, 128, 256)
+
+
+def head_taps(x: torch.Tensor, w_host, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """taps [B,H,W,9] = per-pixel products of a channels-last activation x [B,C,H,W] with the head conv's folded
+    weights `w_host` (a contiguous float32 NumPy array [C,9] on the HOST: it travels as a kernel parameter)."""
+    L = lib()
+    B, C, H, W = x.shape
+    if C not in HEAD_CHANNELS or x.dtype != torch.float32 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("head_taps expects a channels-last fp32 activation with 32/64/128/256 channels")
+    if w_host.dtype.name != "float32" or w_host.shape != (C, 9) or not w_host.flags["C_CONTIGUOUS"]:
+        raise ValueError("w_host must be a C-contiguous float32 [C,9] array")
+    dev = x.device
+    guard = contextlib.nullcontext() if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+    with guard:
+        if out is None:
+            out = torch.empty((B, H, W, 9), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(L.nastar_b200_head_taps(x.data_ptr(), B * H * W, C, w_host.ctypes.data, out.data_ptr(),
+                                       ctypes.c_void_p(stream)), "nastar_b200_head_taps")
+    return out
 
 
 def cost_from_taps(taps: torch.Tensor, bias: float, scale: float) -> torch.Tensor:

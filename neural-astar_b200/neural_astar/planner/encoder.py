@@ -18,6 +18,10 @@ import torch.nn as nn
 # (last, single-output-channel conv) is always fp32.  bench.py states this in its `dtype` field;
 # tests/test_gpu_module_api.py counts how many search masks differ between the two settings.
 ALLOW_TF32 = os.environ.get("NASTAR_B200_ENCODER_TF32", "1") != "0"
+# The head's per-pixel [C] x [C,9] product: the engine's streaming kernel (csrc/nastar_glue.cuh head_taps_kernel, fp32
+# FMA, weights in the constant bank) or, with NASTAR_B200_HEAD_KERNEL=0, torch.mm (cuBLAS SGEMM, 3-4x slower on this
+# skinny shape).  Same sums up to fp32 re-association.
+HEAD_KERNEL = os.environ.get("NASTAR_B200_HEAD_KERNEL", "1") != "0"
 
 
 class EncoderBase(nn.Module):
@@ -30,6 +34,7 @@ class EncoderBase(nn.Module):
         self._plan_key = None
         self._nhwc = False      # conv weights converted to channels-last (done lazily on the first CUDA batch)
         self._head_scalars = (0.0, 1.0)   # (folded bias of the head conv, const) as Python floats
+        self._head_w_host = None          # folded [C,9] weights of the head conv on the host (kernel parameter)
 
     def construct_encoder(self, input_dim: int, encoder_depth: int) -> nn.Module:
         raise NotImplementedError
@@ -79,6 +84,10 @@ class EncoderBase(nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
         wm = plan[-1][7][0]
         B, C, H, W = x.shape
+        if HEAD_KERNEL and self._head_w_host is not None and C in (32, 64, 128, 256):
+            from .. import _native
+
+            return _native.head_taps(x, self._head_w_host, out=out), self._head_scalars[0], self._head_scalars[1]
         a = x.permute(0, 2, 3, 1).reshape(-1, C)
         if out is not None:     # write the GEMM result straight into a caller-owned [B,H,W,9] buffer
             taps = torch.mm(a, wm, out=out.view(-1, 9)).view(B, H, W, 9)
@@ -133,6 +142,8 @@ class EncoderBase(nn.Module):
         last_bias = plan[-1][1]
         self._head_scalars = (float(last_bias.reshape(-1)[0]) if last_bias.numel() == 1 else 0.0,
                               float(self.const) if not isinstance(self.const, float) else self.const)
+        head = plan[-1][7]
+        self._head_w_host = head[0].detach().cpu().numpy().astype("float32", order="C") if head is not None else None
         self._plan, self._plan_key = plan, key
         return plan
 

@@ -63,4 +63,4 @@ class Golden:
 def all_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
                   if "ckpt" not in os.path.basename(p)
-                  and not os.path.basename(p).startswith(("train_curve", "inputs_")))  # search vectors only
+                  and not os.path.basename(p).startswith(("train_curve", "inputs_", "adversarial_")))  # search vectors only

@@ -53,6 +53,20 @@ def test_golden_masks_bit_exact(native, name):
     np.testing.assert_array_equal(ns, g.z["hist_sum"])
 
 
+def test_adversarial_near_tie_engine_equals_spec(native, oracle):
+    """The one documented deviation from the reference (DESIGN.md "Selection semantics"): on the adversarial near-tie
+    vectors the engine — like the SPEC oracle — closes one cell fewer than the reference; everything else agrees."""
+    g = Golden("adversarial_neartie")
+    hist, paths, ts, ns, _ = _run_native(native, g.cost, g.start, g.goal, g.obst, g.g_ratio)
+    spec = oracle.forward(g.cost, g.start, g.goal, g.obst, mode="spec")
+    np.testing.assert_array_equal(hist, spec.histories)
+    np.testing.assert_array_equal(paths, spec.paths)
+    np.testing.assert_array_equal(ns, spec.n_steps)
+    np.testing.assert_array_equal(paths != 0, g.bits("path_bits") != 0)
+    diff = (hist != 0) != (g.bits("hist_bits") != 0)
+    assert diff.reshape(g.B, -1).sum(1).tolist() == [1] * g.B
+
+
 @pytest.mark.parametrize("name", ["mazes032_neural_test", "warcraft12_synth"])
 def test_golden_training_mode_masks(native, name):
     g = Golden(name)

@@ -171,8 +171,8 @@ def test_validation_step_one_launch_matches_two_calls_and_reference_anchor():
         mod.validation_step((maps, start, goal, opt), 0)          # warm-up (plan building, autotuning)
         before = _native.launch_count()
         mod.validation_step((maps, start, goal, opt), 0)
-        # pack_inputs + ONE search launch (both halves)
-        assert _native.launch_count() - before == 2
+        # pack_inputs + head products + ONE search launch (both halves)
+        assert _native.launch_count() - before == 3
         got = tuple(mod.logged[f"metrics/{k}"] for k in ("p_opt", "p_exp", "h_mean"))
         out = na(maps, start, goal)
         va = VanillaAstar().cuda()(maps, start, goal)
@@ -230,6 +230,26 @@ def test_cost_kinds_equal_plane_search(native):
         native.forward(big, big, big, big, 0.5, 64 * 64, cost_kind=native.COST_LOGIT)
 
 
+@pytest.mark.parametrize("C,B,H", [(256, 7, 32), (128, 5, 12), (64, 3, 20), (32, 2, 9)])
+def test_head_taps_kernel_matches_fp32_matmul(native, C, B, H):
+    """Encoder head: per-pixel [C] x [C,9] products from the streaming kernel vs a plain PyTorch fp32 matmul of the
+    same operands (different summation order only)."""
+    torch.manual_seed(C)
+    x = torch.randn(B, C, H, H, device="cuda").contiguous(memory_format=torch.channels_last)
+    w = torch.randn(C, 9, device="cuda") / C ** 0.5
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        want = (x.permute(0, 2, 3, 1).reshape(-1, C).double() @ w.double()).view(B, H, H, 9)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    got = native.head_taps(x, w.cpu().numpy())
+    assert got.shape == (B, H, H, 9)
+    assert float((got.double() - want).abs().max()) < 2e-5
+    buf = torch.empty_like(got)
+    assert native.head_taps(x, w.cpu().numpy(), out=buf).data_ptr() == buf.data_ptr() and torch.equal(buf, got)
+
+
 @pytest.mark.parametrize("C,Hm,H", [(1, 32, 32), (3, 96, 12), (2, 24, 12), (1, 64, 64)])
 def test_pack_inputs_matches_torch(native, C, Hm, H):
     torch.manual_seed(C + Hm)
@@ -272,7 +292,7 @@ def test_fused_forward_equals_unfused_composition(native, arch, inp, depth, cons
         na(x, s, g)             # plan building
         before = native.launch_count()
         out = na(x, s, g, store_intermediate_results=False)
-        assert native.launch_count() - before == 2          # pack_inputs + search; the rest is cuDNN/cuBLAS
+        assert native.launch_count() - before == 3          # pack_inputs + head products + search; the rest is cuDNN
         cost = na.encode(x, s, g)
         passable = torch.ones_like(s) if na.learn_obstacles else x
         want = na.perform_astar(cost, s, g, passable)

@@ -96,6 +96,26 @@ def test_selection_trace_matches_reference(oracle, name):
     assert swapped <= max(1, total // 10000), f"{swapped} exp-collision swaps in {total} selections"
 
 
+def test_adversarial_near_tie_is_the_documented_one_cell_deviation(oracle):
+    """tests/golden/adversarial_neartie.npz: two open cells with f one ulp apart and equal rounded exp.  LITERAL (the
+    reference's own selection rule) must reproduce the reference step for step; SPEC (arg-min over exact f — what the
+    CUDA engine implements, DESIGN.md "Selection semantics") expands the smaller f first, reaches the goal one step
+    earlier and leaves exactly ONE cell — (1,2) — out of `histories`; paths are identical."""
+    g = Golden("adversarial_neartie")
+    ref_h, ref_p = g.bits("hist_bits") != 0, g.bits("path_bits") != 0
+    lit = oracle.forward(g.cost, g.start, g.goal, g.obst, mode="literal", want_trace=True)
+    np.testing.assert_array_equal(lit.histories != 0, ref_h)
+    np.testing.assert_array_equal(lit.paths != 0, ref_p)
+    np.testing.assert_array_equal(lit.trace[:, : g.z["trace"].shape[1]], g.z["trace"])
+    spec = oracle.forward(g.cost, g.start, g.goal, g.obst, mode="spec")
+    np.testing.assert_array_equal(spec.paths != 0, ref_p)
+    diff = (spec.histories != 0) != ref_h
+    y, x = g.meta["extra_cell"]
+    for b in range(g.B):
+        assert diff[b].sum() == 1 and diff[b, 0, y, x] and ref_h[b, 0, y, x] and not spec.histories[b, 0, y, x]
+    np.testing.assert_array_equal(spec.n_steps + 1, g.z["hist_sum"])       # one expansion fewer than the reference
+
+
 @pytest.mark.parametrize("name", ["mazes032_neural_test", "warcraft12_synth"])
 def test_training_mode_forward(oracle, name):
     g = Golden(name)
