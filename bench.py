@@ -393,9 +393,26 @@ def config_c3(dev, peak):
     fwd_us, bwd_us = t_of(fw), t_of(bw)
     algo = 36 * N * B    # 28*N forward + read grad_histories + write grad_cost
     ach = algo / ((fwd_us + bwd_us) * 1e-6) / 1e9
+    # the same pair on 64x64 maps (the reference's all_064 set: tests/golden/all064_vanilla.npz, 12 maps x8), training
+    # cap T = 0.25*64*64: forward on the warp64 engine, backward on the generic engine's event-based closed form
+    g64 = load_problem("all064_vanilla")[3]
+    rep = 8
+    o64, s64, g64t = (torch.from_numpy(np.tile(x, (rep, 1, 1, 1))).to(dev) for x in (g64.obst, g64.start, g64.goal))
+    gen = torch.Generator().manual_seed(7)
+    c64 = (o64.cpu() * (0.3 + 0.7 * torch.rand(o64.shape, generator=gen))).to(dev)
+    T64 = int(0.25 * 64 * 64)
+    fw64 = lambda: _native.forward(c64, s64, g64t, o64, 0.5, T64)  # noqa: E731
+    h64, _, ts64, ns64, _ = fw64()
+    Tb64 = _native.batch_steps(ts64, ns64, T64)
+    gh64 = torch.randn(h64.shape, generator=gen).to(dev) / h64.numel()
+    bw64 = lambda: _native.backward(c64, s64, g64t, o64, gh64, Tb64, ts64, 0.5)  # noqa: E731
+    f64_us, b64_us = t_of(fw64), t_of(bw64)
     return {"workload": "NeuralAstar training step (Tmax=0.25 -> T=256, b=100, RMSprop, L1), mazes_032 first train batch",
             "train_steps_per_s": 1e3 / ms, "maps_per_s": B * 1e3 / ms, "ms_per_step": ms,
             "search_fwd_us": fwd_us, "search_bwd_us": bwd_us,
+            "grid64": {"workload": "search kernels alone, all_064 maps (12 distinct x8 = 96), learned-like costs, T = 1024 cap",
+                       "fwd_us": f64_us, "bwd_us": b64_us, "bwd_over_fwd": b64_us / f64_us,
+                       "engines": "forward: warp64 (engine 4); backward: generic engine, event-based closed form"},
             "roofline": {"bound": "hbm", "kernel": "astar_warp32_kernel<0,0,0> + <0,1,0>", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": algo}}
 

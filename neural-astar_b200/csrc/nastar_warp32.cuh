@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         if (kFused && !cost_plane) {
             // fused encoder hand-off: the cost plane is produced here from the encoder's raw
             // output while the TMA copies of the other planes are in flight
-#pragma unroll 1
+#pragma unroll 4      // four rows of gathers in flight: the prologue is a chain of L2 round trips for one warp
             for (int y = 0; y < H; ++y)
                 S.cost[(y << 5) + lane] = cost_value(cost_kind, gCost, y, lane, H, W, p.cost_bias, p.cost_scale);
         }
