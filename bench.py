@@ -550,8 +550,7 @@ def bench_ours(args):
 
     def loop_dev(n, evs=None):
         for k in range(n):
-            slot = ring[k % ring_n]
-            pipe_dev.submit(slot[0], slot[1], slot[2])
+            pipe_dev.submit_stacked(ring[k % ring_n])
             if evs is not None:
                 evs[k + 1].record()
         return pipe_dev.drain()

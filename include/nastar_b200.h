@@ -151,7 +151,7 @@ int nastar_b200_batch_steps(const int32_t *t_solve, const int32_t *n_steps, int3
 
 /* Which forward engine a shape dispatches to: 1 = warp-resident (H,W <= 32), 4 = warp-resident 64-wide
  * (H,W <= 64), 2 = generic warp engine with shared-memory state, 3 = generic with global-memory state,
- * 0 = unsupported.  (The backward of engine-4 shapes runs on the generic engine.)  Engine-2/3 shapes whose cost
+ * 0 = unsupported.  Engine-2/3 shapes whose cost
  * plane IS the obstacle plane (same pointer and stride: VanillaAstar, astar.py:93-94) are first offered to
  * engine 5, the CTA-per-map binary-cost engine (csrc/nastar_bin16.cuh); maps it cannot take (a cost value
  * outside {0,1}) are re-run by engine 2/3 inside the same call. */

@@ -148,7 +148,7 @@ int nastar_b200_abi_version(void) { return NASTAR_B200_ABI_VERSION; }
 int nastar_b200_engine_for(int32_t H, int32_t W) {
     if (H <= 0 || W <= 0) return 0;
     if (H <= 32 && W <= 32) return 1;
-    if (H <= 64 && W <= 64) return 4;   // forward; the backward of these shapes runs on the generic engine
+    if (H <= 64 && W <= 64) return 4;   // forward and (event-based) backward on the warp-resident 64-wide engine
     return generic_engine_for(H, W);
 }
 
@@ -164,7 +164,7 @@ size_t nastar_b200_forward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
 }
 
 size_t nastar_b200_backward_workspace_bytes(int32_t B, int32_t H, int32_t W) {
-    if (B <= 0 || nastar_b200_engine_for(H, W) == 1) return 0;
+    if (B <= 0 || nastar_b200_engine_for(H, W) == 1 || nastar_b200_engine_for(H, W) == 4) return 0;
     const int e = generic_engine_for(H, W);
     if (e == 0) return 0;
     return size_t(generic_slots(B)) * nastar::GenericLayout(H, W).slot_total(e == 3, true);
@@ -223,10 +223,12 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         if (he != cudaSuccess) return cuda_fail(he);
         const bool noexit = (p->flags & NASTAR_FWD_NO_EARLY_EXIT) != 0;
         const size_t smem = sizeof(nastar::W64Smem);
+        nastar::W64Args wa{};
+        wa.f = *p;
         auto launch = [&](auto kernel) -> cudaError_t {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if (e != cudaSuccess) return e;
-            kernel<<<p->B, 32, smem, stream>>>(*p);
+            kernel<<<p->B, 32, smem, stream>>>(wa);
             return cudaSuccess;
         };
         cudaError_t e;
@@ -308,7 +310,36 @@ int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
     if (p->B <= 0 || p->H <= 0 || p->W <= 0) return NASTAR_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     int engine = nastar_b200_engine_for(p->H, p->W);
-    if (engine != 1) engine = generic_engine_for(p->H, p->W);   // warp64 shapes: backward on the generic engine
+    if (engine == 4) {
+        // warp-resident 64-wide engine: event-based closed form next to the forward state in shared memory
+        cudaError_t he = ensure_heur64(stream);
+        if (he != cudaSuccess) return cuda_fail(he);
+        nastar::W64Args wa{};
+        wa.f.cost = p->cost;   wa.f.cost_stride = p->cost_stride;
+        wa.f.start = p->start; wa.f.start_stride = p->start_stride;
+        wa.f.goal = p->goal;   wa.f.goal_stride = p->goal_stride;
+        wa.f.obst = p->obst;   wa.f.obst_stride = p->obst_stride;
+        wa.f.B = p->B; wa.f.H = p->H; wa.f.W = p->W;
+        wa.f.g_ratio = p->g_ratio;
+        wa.f.one_minus_g_ratio = p->one_minus_g_ratio;
+        wa.f.T = 0;   // the loop bound comes from *T_batch on the device
+        wa.sqrt_w = p->sqrt_w;
+        wa.T_batch = p->T_batch;
+        wa.t_solve_in = p->t_solve;
+        wa.grad_hist = p->grad_histories;
+        wa.grad_stride = p->grad_stride;
+        wa.grad_cost = p->grad_cost;
+        const size_t smem = sizeof(nastar::W64Smem) + sizeof(nastar::W64Bwd);
+        cudaError_t e = cudaFuncSetAttribute(nastar::astar_warp64_kernel<false, false, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return cuda_fail(e);
+        nastar::astar_warp64_kernel<false, false, true><<<p->B, 32, smem, stream>>>(wa);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e);
+        return NASTAR_OK;
+    }
+    if (engine != 1) engine = generic_engine_for(p->H, p->W);
     if (engine == 0) return NASTAR_EUNSUPPORTED;
     if (engine >= 2) {
         const nastar::GenericLayout L(p->H, p->W);

@@ -9,7 +9,12 @@
 //   * expansion: of a lane's two rows at most one is within r-1..r+1, so the row lanes pick that slot
 //     with selects and run the same branch-free 3-cell mask algebra on 64-bit masks;
 //   * rescan of row r: every lane checks columns l and l+32.
-// The backward for these shapes stays on the generic engine.
+// kBwd = true replays the same state machine for *T_batch steps and evaluates the closed-form gradient
+// EVENT-BASED, like the generic engine (nastar_generic.cuh): a cell's softmax weight v = exp(-f/sqrt(W)) only changes
+// when the cell is opened, relaxed or closed, so its contribution over an interval of constant v is
+// v * (Gh * (A(t1)-A(t0)) - (B(t1)-B(t0))) with A, B the prefix sums of 1/S_t and D_t/S_t^2 (S = sum of v over the open
+// set, D = <Gh, v>, both maintained in fp64 from the <= 10 events of a step).  Per-cell v / A(t0) / B(t0) / acc and
+// the upstream gradient live in shared memory next to the forward state (198 KB per map).
 #pragma once
 #include "../../include/nastar_b200.h"
 #include "nastar_common.cuh"
@@ -37,10 +42,33 @@ struct __align__(16) W64Smem {
     unsigned long long bar;
 };
 
-template <bool kTrace, bool kNoExit>
-__global__ void __launch_bounds__(32) astar_warp64_kernel(const nastar_fwd_params p) {
+// backward-only shared-memory planes (dynamic shared memory right behind W64Smem)
+struct __align__(16) W64Bwd {
+    double acc[kCells64];   // closed intervals: sum of v * (Gh * dA - dB)
+    double a0[kCells64];    // A(t0), B(t0) of the cell's current open interval
+    double b0[kCells64];
+    float v[kCells64];      // current softmax numerator of the cell, 0 if it is not open
+    float gh[kCells64];     // upstream gradient dL/dhistories (goal zeroed when the clamp blocks it)
+};
+
+// forward parameters + the extra fields of nastar_bwd_params (same idea as W32Args)
+struct W64Args {
+    nastar_fwd_params f;
+    float sqrt_w;
+    const int32_t* T_batch;
+    const int32_t* t_solve_in;
+    const float* grad_hist;
+    int64_t grad_stride;
+    float* grad_cost;
+};
+
+template <bool kTrace, bool kNoExit, bool kBwd = false>
+__global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
+    constexpr bool kContinue = kBwd || kNoExit;
+    const nastar_fwd_params& p = a.f;
     extern __shared__ __align__(16) unsigned char smem64_raw[];
     W64Smem& S = *reinterpret_cast<W64Smem*>(smem64_raw);
+    W64Bwd& Bw = *reinterpret_cast<W64Bwd*>(smem64_raw + sizeof(W64Smem));
     float2* const sGH = S.ghbuf + 2;
     const int lane = threadIdx.x;
     const int b = blockIdx.x;
@@ -156,10 +184,36 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const nastar_fwd_param
     }
     S.open_row[lane] = open[0];
     S.open_row[lane + 32] = open[1];
+    // backward state: running sums replicated in every lane
+    double Ssum = 0.0, Dsum = 0.0, Acum = 0.0, Bcum = 0.0;
+    int Tb = 0, ts_in = NASTAR_TS_CAPPED;
+    if (kBwd) {
+        Tb = *a.T_batch;
+        ts_in = a.t_solve_in[b];
+        // clamp(hist + sel) blocks the gradient at a goal that is re-selected after its solve step
+        // (pre-clamp value 2, differentiable_astar.py:222-223)
+        const bool blocked = (ts_in >= 0) && (ts_in < Tb - 1);
+        const float* gG = a.grad_hist + int64_t(b) * a.grad_stride;
+        for (int i = lane; i < kCells64; i += 32) {
+            const int y = i >> 6, x = i & 63;
+            Bw.acc[i] = 0.0;
+            Bw.v[i] = 0.f;
+            Bw.gh[i] = (y < H && x < W && !(blocked && i == goal_rc)) ? __ldg(gG + y * W + x) : 0.f;
+        }
+        __syncwarp();
+        if (start_rc >= 0) {
+            const float f0 = f_value(gr, omg, 0.f, sGH[start_rc].y);
+            const float v0 = expf(__fdiv_rn(-f0, a.sqrt_w));                 // :207
+            if (lane == 0) { Bw.v[start_rc] = v0; Bw.a0[start_rc] = 0.0; Bw.b0[start_rc] = 0.0; }
+            Ssum = double(v0);
+            Dsum = double(Bw.gh[start_rc]) * Ssum;
+        }
+    }
     __syncwarp();
 
     // ---------------- search loop --------------------------------------------------------------
-    const int T = p.T;
+    const int T = kBwd ? Tb : p.T;
+    const bool stationary_ok = (gr >= 0.5f);   // post-solve steps are stationary
     int t_solve = NASTAR_TS_CAPPED;
     int32_t* trace = kTrace ? (p.trace + int64_t(b) * T) : nullptr;
     int t = 0;
@@ -170,13 +224,26 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const nastar_fwd_param
         if (rm_key[1] < bk) { bk = rm_key[1]; bid = ((lane + 32) << 6) | rm_col[1]; }
         const uint32_t m = __reduce_min_sync(kFull, bk);
         if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
+        double A1 = 0.0, B1 = 0.0;   // prefix sums INCLUDING step t (the events of step t act from t+1 on)
+        if (kBwd) {
+            const double inv = 1.0 / Ssum;
+            const double a_t = inv, b_t = Dsum * inv * inv;
+            if (stationary_ok && (ts_in >= 0) && (t == ts_in + 1)) {
+                // solved: the goal is re-selected with a frozen open set until step T_batch-1
+                Acum += double(Tb - t) * a_t;
+                Bcum += double(Tb - t) * b_t;
+                break;
+            }
+            A1 = Acum + a_t;
+            B1 = Bcum + b_t;
+        }
         const uint32_t ind = __reduce_min_sync(kFull, (bk == m) ? uint32_t(bid) : 0xFFFFFFFFu);
         const int r = int(ind >> 6), c = int(ind & 63u);
         if (kTrace && lane == 0) trace[t] = r * W + c;
         const bool solved = (int(ind) == goal_rc);
         const u64 m1 = 1ull << c, m0 = m1 >> 1, m2 = m1 << 1;
         // rescan inputs: columns lane and lane+32 of row r
-        const u64 open_r = (kNoExit && solved) ? S.open_row[r] : (S.open_row[r] & ~m1);
+        const u64 open_r = (kContinue && solved) ? S.open_row[r] : (S.open_row[r] & ~m1);
         const uint32_t ka = S.key[(r << 6) + lane], kb = S.key[(r << 6) + 32 + lane];
         uint32_t rs_key = ((open_r >> lane) & 1ull) ? ka : kKeyInf;
         int rs_col = lane;
@@ -221,6 +288,30 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const nastar_fwd_param
         if (u0) { sGH[cell - 1].x = g2; S.key[cell - 1] = q0; S.par[cell - 1] = int8_t(off); }
         if (u1) { sGH[cell].x = g2;     S.key[cell] = q1;     S.par[cell] = int8_t(off + 1); }
         if (u2) { sGH[cell + 1].x = g2; S.key[cell + 1] = q2; S.par[cell + 1] = int8_t(off + 2); }
+        if (kBwd) {
+            double dS = 0.0, dD = 0.0;   // this lane's change of S and D
+            auto event = [&](int cl, float v_new) {
+                const float v_old = Bw.v[cl];
+                const double gh = double(Bw.gh[cl]);
+                if (v_old != 0.f) Bw.acc[cl] += double(v_old) * (gh * (A1 - Bw.a0[cl]) - (B1 - Bw.b0[cl]));
+                Bw.v[cl] = v_new;
+                Bw.a0[cl] = A1;
+                Bw.b0[cl] = B1;
+                const double dv = double(v_new) - double(v_old);
+                dS += dv;
+                dD += gh * dv;
+            };
+            if (u0) event(cell - 1, expf(__fdiv_rn(-f0n, a.sqrt_w)));     // :207
+            if (u1) event(cell, expf(__fdiv_rn(-f1n, a.sqrt_w)));
+            if (u2) event(cell + 1, expf(__fdiv_rn(-f2n, a.sqrt_w)));
+            if (isr && !solved) event(int(ind), 0.f);                      // the selected cell leaves the open set
+            // the events sit on the (at most three) lanes that own rows r-1, r, r+1
+            const int l0 = (r - 1) & 31, l1 = r & 31, l2 = (r + 1) & 31;
+            Ssum += __shfl_sync(kFull, dS, l0) + __shfl_sync(kFull, dS, l1) + __shfl_sync(kFull, dS, l2);
+            Dsum += __shfl_sync(kFull, dD, l0) + __shfl_sync(kFull, dD, l1) + __shfl_sync(kFull, dD, l2);
+            Acum = A1;
+            Bcum = B1;
+        }
         const uint32_t k0 = u0 ? q0 : kKeyInf, k1 = u1 ? q1 : kKeyInf, k2 = u2 ? q2 : kKeyInf;
         uint32_t fk = k0;
         int fc = c - 1;
@@ -233,7 +324,7 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const nastar_fwd_param
             S.open_row[myrow] = myopen;
         }
         if (solved && t_solve < 0) t_solve = t;
-        if (!kNoExit && solved) break;
+        if (!kContinue && solved) break;
         // fold the rescan into the cached minimum of row r (lane r&31, slot r>>5)
         const uint32_t mr = __reduce_min_sync(kFull, rs_key);
         const uint32_t mc = __reduce_min_sync(kFull, (rs_key == mr) ? uint32_t(rs_col) : 0xFFFFFFFFu);
@@ -247,7 +338,23 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const nastar_fwd_param
         __syncwarp();
     }
     __syncwarp();
-    const int steps = (!kNoExit && t_solve >= 0) ? (t + 1) : t;
+    const int steps = (!kContinue && t_solve >= 0) ? (t + 1) : t;
+
+    if (kBwd) {
+        // close the intervals of the cells still open, scale: dL/dcost = -(1-g_ratio)/sqrt(W) * acc
+        const double coef = -double(omg) / double(a.sqrt_w);
+        float* gOut = a.grad_cost + int64_t(b) * N;
+        for (int i = lane; i < kCells64; i += 32) {
+            const int y = i >> 6, x = i & 63;
+            if (y < H && x < W) {
+                double acc = Bw.acc[i];
+                const float v = Bw.v[i];
+                if (v != 0.f) acc += double(v) * (double(Bw.gh[i]) * (Acum - Bw.a0[i]) - (Bcum - Bw.b0[i]));
+                gOut[y * W + x] = float(coef * acc);
+            }
+        }
+        return;
+    }
 
     // ---------------- backtrack ------------------------------------------------------------------
     u64 path0 = 0ull, path1 = 0ull;

@@ -153,7 +153,14 @@ class PipelinedPlanner:
         dev = _check_planner(planner, map_designs)
         self.planner, self.device, self.host = planner, dev, host
         examples = (map_designs, start_maps, goal_maps)
-        self._in = [tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in examples) for _ in range(2)]
+        # when the three inputs share shape and dtype (the "m+" planners) they live in ONE stacked buffer per
+        # parity, so a whole batch can arrive with a single copy (submit_stacked)
+        self._stacked = None
+        if all(t.shape == map_designs.shape and t.dtype == map_designs.dtype for t in examples):
+            self._stacked = [torch.empty((3,) + tuple(map_designs.shape), dtype=map_designs.dtype, device=dev) for _ in range(2)]
+            self._in = [tuple(st[i] for i in range(3)) for st in self._stacked]
+        else:
+            self._in = [tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in examples) for _ in range(2)]
         for buf in self._in:
             for dst, src in zip(buf, examples):
                 dst.copy_(src)
@@ -249,6 +256,20 @@ class PipelinedPlanner:
         kind = "enc" if self._k == 0 else "full"
         g = self._graph(kind, par)
         g.replay()
+        self.replays += 1
+        self.native_launches += self._per_graph[(kind, par)]
+        self._k += 1
+        return self._outs[(kind, par)]
+
+    def submit_stacked(self, batch: torch.Tensor) -> Optional[AstarOutput]:
+        """submit() for a batch delivered as one [3, B, 1, H, W] tensor (map_designs, start_maps, goal_maps stacked):
+        a single device copy instead of three."""
+        if self._stacked is None or self.host:
+            raise ValueError("submit_stacked needs equally shaped inputs and a device-input pipeline")
+        par = self._k & 1
+        self._stacked[par].copy_(batch, non_blocking=True)
+        kind = "enc" if self._k == 0 else "full"
+        self._graph(kind, par).replay()
         self.replays += 1
         self.native_launches += self._per_graph[(kind, par)]
         self._k += 1

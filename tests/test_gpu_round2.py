@@ -370,6 +370,14 @@ def test_pipelined_and_host_graphs_match_eager():
     assert len(got) == 5
     for (h, p), w in zip(got, want):
         assert torch.equal(h, w.histories) and torch.equal(p, w.paths)
+    # stacked delivery (one copy per batch)
+    prev = None
+    for k, b in enumerate(batches[:3]):
+        prev = pipe.submit_stacked(torch.stack(b))
+        if k >= 1:
+            assert torch.equal(prev.histories, want[k - 1].histories)
+    last = pipe.drain()
+    assert torch.equal(last.histories, want[2].histories) and torch.equal(last.paths, want[2].paths)
     # host pipeline: pinned in, pinned out, copies inside the graphs
     pipe = PipelinedPlanner(na, maps, start, goal, host=True)
     results = []
