@@ -76,7 +76,9 @@ def test_engine_dispatch_and_workspace(built_lib):
     assert L.nastar_b200_forward_workspace_bytes(8, 32, 32) == 0
     assert L.nastar_b200_forward_workspace_bytes(4, 256, 256) >= 4 * 256 * 256 * 9
     assert L.nastar_b200_forward_workspace_bytes(4, 64, 64) == 0
-    assert L.nastar_b200_backward_workspace_bytes(4, 64, 64) >= 4 * 64 * 64 * 12   # backward of 64x64: generic engine
+    assert L.nastar_b200_backward_workspace_bytes(4, 64, 64) == 0       # backward of 64x64: warp64 engine, all in shared memory
+    assert L.nastar_b200_backward_workspace_bytes(4, 96, 64) >= 4 * 96 * 64 * 28     # generic engine: 28 B per cell
+    assert L.nastar_b200_bin16_supported(256, 256) == 1 and L.nastar_b200_bin16_supported(64, 64) == 0
     assert L.nastar_b200_backward_workspace_bytes(4, 32, 32) == 0
     assert L.nastar_b200_status_string(2).decode().startswith("unsupported")
 
