@@ -44,6 +44,18 @@ N_CELLS = H * W
 ALGO_BYTES_PER_MAP = 28 * N_CELLS  # read cost+start+goal+obstacles, write histories(f32)+paths(i64)
 WORKLOAD = "NeuralAstar inference, mazes_032_moore_c8 32x32, batch=100 (BASELINE.json configs[1])"
 DATA = "mazes_032_moore_c8 test split (100 maps, seed-1234 starts) + shipped checkpoint, committed fixtures"
+RING_N = 112   # 112 x 1.2 MB of inputs = 138 MB > 126 MB L2: a step's inputs are never L2-resident
+
+
+def shared_config(world: int) -> dict:
+    """`config` of the JSON line — identical in both arms (ours / --impl reference) so the two lines are comparable."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "grid": "32x32", "g_ratio": 0.5, "T_max": W * W,
+            "parallelism": f"dp{world} (independent map shards, no data-path collective; the reference arm runs on rank 0's "
+                           f"host cores only)",
+            "l2": f"GPU arm: inputs rotate through a ring of {RING_N} device-resident batches (138 MB > 126 MB L2), or come "
+                  f"from pinned host memory every step (e2e); not applicable to the CPU reference arm",
+            "timing": "GPU arm: CUDA events around the whole K-step loop (pipeline fill + drain inside), barrier + "
+                      "synchronize both sides, max over ranks; reference arm: host wall clock"}
 
 
 def _paths(ours: bool):
@@ -264,8 +276,7 @@ def bench_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": DATA,
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "grid": "32x32", "g_ratio": 0.5, "T_max": W * W},
-        "timing": "host wall clock (CPU implementation)",
+        "config": shared_config(args.gpus),
         "expansions_per_s": hist_sum * args.steps / dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -540,7 +551,7 @@ def bench_ours(args):
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # ---- the two timed legs: pipelined planner, device-resident ring / pinned host buffers -----------------------
-    ring_n = 112   # 112 x 1.2 MB of inputs = 138 MB > 126 MB L2: a step's inputs are never L2-resident
+    ring_n = RING_N
     ring = torch.stack([torch.stack([t.roll(i, 0) for t in (maps, start, goal)]) for i in range(ring_n)])
     pipe_dev = PipelinedPlanner(planner, maps, start, goal)
     pipe_host = PipelinedPlanner(planner, maps, start, goal, host=True)
@@ -655,14 +666,10 @@ def bench_ours(args):
             "dtype": "f32 search (bit-exact masks) / " + ("tf32" if _enc.ALLOW_TF32 else "fp32")
                      + " encoder 3x3 convs (cuDNN tensor cores, torch's default), fp32 head",
             "data": DATA,
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "grid": "32x32", "g_ratio": 0.5, "T_max": W * W,
-                       "parallelism": f"dp{world} (independent map shards, no data-path collective)",
-                       "api": "neural_astar.utils.inference.PipelinedPlanner (one CUDA-graph launch per step: search of "
-                              "batch k || encoder of batch k+1)",
-                       "l2": f"inputs rotate through a ring of {ring_n} device-resident batches (138 MB > 126 MB L2)",
-                       "timing": "CUDA events around the whole K-step loop (pipeline fill + drain inside), barrier + "
-                                 "synchronize both sides, max over ranks",
-                       "rank_cpu_affinity": pinned_cpus},
+            "config": shared_config(world),
+            "api": "neural_astar.utils.inference.PipelinedPlanner (one CUDA-graph launch per step: search of batch k || "
+                   "encoder of batch k+1)",
+            "rank_cpu_affinity": pinned_cpus,
             "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": step_max,
             "expansions_per_s": expansions * K / (total_ms * 1e-3),
             "search_kernel_us": kern_s * 1e6,
