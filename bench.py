@@ -508,6 +508,12 @@ def config_c5(dev, peak, rank, timer, dist, world):
         ms, exp_total, exp_max, solved = (float(v) for v in stats)
     maps_total = per_gpu * world
     algo = 24 * Hh * Ww * per_gpu     # cost aliases obstacles: 24*N bytes per map
+    traffic = None                    # DRAM bytes per launch from the committed ncu capture (296 maps), scaled to this batch
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_bin16_v3.json")))
+        traffic = prof["dram_bytes_per_launch"] / 296.0 * per_gpu
+    except Exception:
+        pass
     ach = algo / (ms * 1e-3) / 1e9
     return {"workload": f"VanillaAstar, synthetic 256x256 Moore grids (p_obst 0.2, Chebyshev(start,goal) >= 128), "
                         f"{per_gpu} distinct maps per GPU x {world} GPU(s), seed 1234+rank",
@@ -518,7 +524,9 @@ def config_c5(dev, peak, rank, timer, dist, world):
                       and os.environ.get("NASTAR_B200_BIN16", "1") != "0" else "3 (generic, HBM workspace)",
             "map_generation_s_per_rank": gen_s,
             "roofline": {"bound": "hbm", "kernel": "astar_bin16_kernel<8>", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "algorithmic_bytes_per_launch": algo, "per_gpu": True}}
+                         "frac": ach / peak, "algorithmic_bytes_per_launch": algo, "traffic": traffic, "per_gpu": True,
+                         "note": "latency-bound: the launch lasts as long as its longest map (one dependent step chain per "
+                                 "map); see us_per_step_longest_map"}}
 
 
 def bench_ours(args):

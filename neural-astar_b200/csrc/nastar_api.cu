@@ -396,8 +396,14 @@ int nastar_b200_backward(const nastar_bwd_params* p, void* stream_v) {
     a.grad_hist = p->grad_histories;
     a.grad_stride = p->grad_stride;
     a.grad_cost = p->grad_cost;
-    // dynamic shared memory = the dense softmax-numerator plane v (padded 32x32 fp32)
-    nastar::astar_warp32_kernel<false, true><<<p->B, 32, nastar::kCells * sizeof(float), stream>>>(a);
+    // dynamic shared memory = the per-cell interval state of the event-based closed form (W32Bwd, 32 KB); with the
+    // 17.4 KB of static planes that is above the 48 KB default, hence the opt-in
+    {
+        cudaError_t ea = cudaFuncSetAttribute(nastar::astar_warp32_kernel<false, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(nastar::W32Bwd)));
+        if (ea != cudaSuccess) return cuda_fail(ea);
+    }
+    nastar::astar_warp32_kernel<false, true><<<p->B, 32, sizeof(nastar::W32Bwd), stream>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);

@@ -17,7 +17,9 @@
 //   * planes are staged with 1-D TMA bulk copies (cp.async.bulk + mbarrier) when W == 32 and
 //     results leave as coalesced 128-bit stores; the loop itself never touches HBM.
 //   kBwd = true replays the same state machine and accumulates the closed-form gradient of the
-//   straight-through softmax — same code path, so the replay cannot drift.
+//   straight-through softmax — same code path, so the replay cannot drift; the
+//   accumulation is event-based (a cell's softmax weight only changes when it is opened, relaxed or
+//   closed: per-cell interval bookkeeping against fp64 prefix sums, O(1) per step).
 #pragma once
 #include "../../include/nastar_b200.h"
 #include "nastar_common.cuh"
@@ -54,6 +56,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// backward-only planes (dynamic shared memory), event-based closed form (see nastar_generic.cuh / DESIGN.md):
+struct __align__(16) W32Bwd {
+    double acc[kCells];   // closed intervals: sum of v * (Gh * dA - dB)
+    double a0[kCells];    // A(t0), B(t0) of the cell's current open interval
+    double b0[kCells];
+    float v[kCells];      // softmax numerator exp(-f/sqrt(W)) of open cells, else 0
+    float gh[kCells];     // upstream gradient (goal zeroed when the clamp blocks it)
+};
+
 struct __align__(16) W32Smem {
     float cost[kCells];        // staged cost plane (padded)
     uint32_t key[kCells];      // order-preserving key of f = g_ratio*g + (1-g_ratio)*h, opened cells only
@@ -73,7 +84,8 @@ template <bool kTrace, bool kBwd, bool kNoExit = false, bool kFused = false>
 __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     constexpr bool kContinue = kBwd || kNoExit;   // the loop does not stop at the solve step
     __shared__ W32Smem S;
-    extern __shared__ __align__(16) float sV[];  // backward only: v = exp(-f/sqrt(W)) of open cells, else 0
+    extern __shared__ __align__(16) unsigned char bwd_raw[];  // backward only: W32Bwd
+    W32Bwd& Bw = *reinterpret_cast<W32Bwd*>(bwd_raw);
     const nastar_fwd_params& p = a.f;
     float2* const sGH = S.ghbuf + 2;
     const int lane = threadIdx.x;
@@ -184,37 +196,22 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     uint32_t rm_key = kKeyInf;
     int rm_col = 0;
 
-    float Gh[32], acc[32];  // backward: upstream gradient / accumulator of cell 4*(lane+32j)+e (padded id)
+    // backward: running sums replicated in every lane (S = sum of v over the open set, D = <Gh, v>, A / B = prefix
+    // sums of 1/S and D/S^2 over the executed steps)
+    double Ssum = 0.0, Dsum = 0.0, Acum = 0.0, Bcum = 0.0;
     int Tb = 0, ts_in = NASTAR_TS_CAPPED;
     if (kBwd) {
-        float4* sV4 = reinterpret_cast<float4*>(sV);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sV4[lane + 32 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
         Tb = *a.T_batch;
         ts_in = a.t_solve_in[b];
         const float* gG = a.grad_hist + int64_t(b) * a.grad_stride;
-        const bool vec = (W == 32) && aligned16(gG);
         // clamp(hist + sel) blocks the gradient at a goal that is re-selected after its solve step
         // (pre-clamp value 2, differentiable_astar.py:222-223)
         const bool blocked = (ts_in >= 0) && (ts_in < Tb - 1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int p0 = 4 * (lane + 32 * j);
-            const int y = p0 >> 5, x0 = p0 & 31;
-            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vec) {
-                if (y < H) g4 = __ldg(reinterpret_cast<const float4*>(gG + p0));
-            } else if (y < H) {
-                if (x0 + 0 < W) g4.x = __ldg(gG + y * W + x0 + 0);
-                if (x0 + 1 < W) g4.y = __ldg(gG + y * W + x0 + 1);
-                if (x0 + 2 < W) g4.z = __ldg(gG + y * W + x0 + 2);
-                if (x0 + 3 < W) g4.w = __ldg(gG + y * W + x0 + 3);
-            }
-            Gh[4 * j + 0] = (blocked && p0 + 0 == goal_rc) ? 0.f : g4.x;
-            Gh[4 * j + 1] = (blocked && p0 + 1 == goal_rc) ? 0.f : g4.y;
-            Gh[4 * j + 2] = (blocked && p0 + 2 == goal_rc) ? 0.f : g4.z;
-            Gh[4 * j + 3] = (blocked && p0 + 3 == goal_rc) ? 0.f : g4.w;
-            acc[4 * j + 0] = acc[4 * j + 1] = acc[4 * j + 2] = acc[4 * j + 3] = 0.f;
+        for (int y = 0; y < 32; ++y) {
+            const int i = (y << 5) + lane;
+            Bw.acc[i] = 0.0;
+            Bw.v[i] = 0.f;
+            Bw.gh[i] = (y < H && lane < W && !(blocked && i == goal_rc)) ? __ldg(gG + y * W + lane) : 0.f;
         }
         __syncwarp();
     }
@@ -223,7 +220,7 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         const float f0 = f_value(gr, omg, 0.f, sGH[start_rc].y);
         if (lane == 0) {
             S.key[start_rc] = fkey(f0);              // g = 0 already (:193)
-            if (kBwd) sV[start_rc] = expf(__fdiv_rn(-f0, a.sqrt_w));  // :207
+            if (kBwd) { Bw.v[start_rc] = expf(__fdiv_rn(-f0, a.sqrt_w)); Bw.a0[start_rc] = 0.0; Bw.b0[start_rc] = 0.0; }  // :207
         }
         if (lane == (start_rc >> 5)) {
             open = 1u << (start_rc & 31);            // open_maps = start_maps (:187)
@@ -233,6 +230,10 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     }
     S.open_row[lane] = open;
     __syncwarp();
+    if (kBwd && start_rc >= 0) {
+        Ssum = double(Bw.v[start_rc]);
+        Dsum = double(Bw.gh[start_rc]) * Ssum;
+    }
 
     // ---------------- the search loop (differentiable_astar.py:203-252) --------------------
     const int T = kBwd ? Tb : p.T;
@@ -247,35 +248,18 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         // -- select: lexicographic arg-min of (f key, row, col) with two REDUX.MINs -----------
         const uint32_t m = __reduce_min_sync(kFull, rm_key);
         if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
+        double A1 = 0.0, B1 = 0.0;   // prefix sums INCLUDING step t (the events of step t act from t+1 on)
         if (kBwd) {
-            // y_t = v / sum(v) over the open set at the START of step t; accumulate
-            // y_t[p] * (Gh[p] - <Gh, y_t>)  (times the number of identical post-solve steps)
-            const float4* sV4 = reinterpret_cast<const float4*>(sV);
-            float4 v[8];
-            float s_ = 0.f, d_ = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[j] = sV4[lane + 32 * j];
-                s_ += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-                d_ = fmaf(Gh[4 * j + 0], v[j].x, d_);
-                d_ = fmaf(Gh[4 * j + 1], v[j].y, d_);
-                d_ = fmaf(Gh[4 * j + 2], v[j].z, d_);
-                d_ = fmaf(Gh[4 * j + 3], v[j].w, d_);
+            const double inv = 1.0 / Ssum;
+            const double a_t = inv, b_t = Dsum * inv * inv;
+            if (stationary_ok && (ts_in >= 0) && (t == ts_in + 1)) {
+                // solved: the goal is re-selected with a frozen open set until step T_batch-1 (App. A.4)
+                Acum += double(Tb - t) * a_t;
+                Bcum += double(Tb - t) * b_t;
+                break;
             }
-            s_ = warp_sum(s_);
-            d_ = warp_sum(d_);
-            const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
-            const float wgt = last ? float(Tb - t) : 1.f;
-            const float inv = wgt / s_;
-            const float dd = d_ / s_;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[4 * j + 0] = fmaf(v[j].x * inv, Gh[4 * j + 0] - dd, acc[4 * j + 0]);
-                acc[4 * j + 1] = fmaf(v[j].y * inv, Gh[4 * j + 1] - dd, acc[4 * j + 1]);
-                acc[4 * j + 2] = fmaf(v[j].z * inv, Gh[4 * j + 2] - dd, acc[4 * j + 2]);
-                acc[4 * j + 3] = fmaf(v[j].w * inv, Gh[4 * j + 3] - dd, acc[4 * j + 3]);
-            }
-            if (last) break;
+            A1 = Acum + a_t;
+            B1 = Bcum + b_t;
         }
         const uint32_t ind = __reduce_min_sync(kFull, (rm_key == m) ? uint32_t((lane << 5) | rm_col) : 0xFFFFFFFFu);
         const int r = int(ind >> 5), c = int(ind & 31u);
@@ -302,7 +286,6 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
             closed |= m1;
             if (!solved) open &= ~m1;                       // the goal stays open once selected
             rm_key = kKeyInf;                               // this row's minimum is rebuilt below
-            if (kBwd && !solved) sV[ind] = 0.f;             // left the open set: no softmax weight
         }
         // -- expansion (:228-249) as mask algebra on this lane's row ---------------------------
         //    idx = ((1-open)(1-hist) + open*(g > g2)) * neighbours * obstacles   (:235-236)
@@ -323,9 +306,31 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         if (u1) { sGH[cell].x = g2;     S.key[cell] = q1;     S.par[cell] = int8_t(off + 1); }
         if (u2) { sGH[cell + 1].x = g2; S.key[cell + 1] = q2; S.par[cell + 1] = int8_t(off + 2); }
         if (kBwd) {
-            if (u0) sV[cell - 1] = expf(__fdiv_rn(-f0n, a.sqrt_w));   // :207
-            if (u1) sV[cell] = expf(__fdiv_rn(-f1n, a.sqrt_w));
-            if (u2) sV[cell + 1] = expf(__fdiv_rn(-f2n, a.sqrt_w));
+            double dS = 0.0, dD = 0.0;   // this lane's change of S and D
+            auto event = [&](int cl, float v_new) {
+                const float v_old = Bw.v[cl];
+                const double gh = double(Bw.gh[cl]);
+                if (v_old != 0.f) Bw.acc[cl] += double(v_old) * (gh * (A1 - Bw.a0[cl]) - (B1 - Bw.b0[cl]));
+                Bw.v[cl] = v_new;
+                Bw.a0[cl] = A1;
+                Bw.b0[cl] = B1;
+                const double dv = double(v_new) - double(v_old);
+                dS += dv;
+                dD += gh * dv;
+            };
+            if (u0) event(cell - 1, expf(__fdiv_rn(-f0n, a.sqrt_w)));   // :207
+            if (u1) event(cell, expf(__fdiv_rn(-f1n, a.sqrt_w)));
+            if (u2) event(cell + 1, expf(__fdiv_rn(-f2n, a.sqrt_w)));
+            if (isr && !solved) event(int(ind), 0.f);                    // the selected cell leaves the open set
+            // the events sit on the lanes of rows r-1, r, r+1
+            const double s0 = __shfl_sync(kFull, dS, max(r - 1, 0)), s1 = __shfl_sync(kFull, dS, r),
+                         s2 = __shfl_sync(kFull, dS, min(r + 1, 31));
+            const double d0 = __shfl_sync(kFull, dD, max(r - 1, 0)), d1 = __shfl_sync(kFull, dD, r),
+                         d2 = __shfl_sync(kFull, dD, min(r + 1, 31));
+            Ssum += (r > 0 ? s0 : 0.0) + s1 + (r < 31 ? s2 : 0.0);
+            Dsum += (r > 0 ? d0 : 0.0) + d1 + (r < 31 ? d2 : 0.0);
+            Acum = A1;
+            Bcum = B1;
         }
         // fold the fresh keys (ascending column, strict < keeps the lowest column on ties)
         const uint32_t k0 = u0 ? q0 : kKeyInf, k1 = u1 ? q1 : kKeyInf, k2 = u2 ? q2 : kKeyInf;
@@ -350,23 +355,17 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
     const int steps = (!kContinue && t_solve >= 0) ? (t + 1) : t;
 
     if (kBwd) {
-        // dL/dcost = -(1-g_ratio)/sqrt(W) * acc   (h = heuristic + cost, f = g_ratio*g + (1-g_ratio)*h)
-        const float coef = -omg / a.sqrt_w;
+        // close the intervals of the cells still open; dL/dcost = -(1-g_ratio)/sqrt(W) * acc
+        // (h = heuristic + cost, f = g_ratio*g + (1-g_ratio)*h)
+        const double coef = -double(omg) / double(a.sqrt_w);
         float* gOut = a.grad_cost + int64_t(b) * N;
-        const bool vec = (W == 32) && aligned16(gOut);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int p0 = 4 * (lane + 32 * j);
-            const int y = p0 >> 5, x0 = p0 & 31;
-            if (y < H) {
-                if (vec) {
-                    *reinterpret_cast<float4*>(gOut + p0) =
-                        make_float4(coef * acc[4 * j], coef * acc[4 * j + 1], coef * acc[4 * j + 2], coef * acc[4 * j + 3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (x0 + e < W) gOut[y * W + x0 + e] = coef * acc[4 * j + e];
-                }
+        for (int y = 0; y < H; ++y) {
+            const int i = (y << 5) + lane;
+            if (lane < W) {
+                double acc = Bw.acc[i];
+                const float v = Bw.v[i];
+                if (v != 0.f) acc += double(v) * (double(Bw.gh[i]) * (Acum - Bw.a0[i]) - (Bcum - Bw.b0[i]));
+                gOut[y * W + lane] = float(coef * acc);
             }
         }
         return;
