@@ -65,6 +65,21 @@ __device__ __forceinline__ float cost_value(int kind, const float* __restrict__ 
     return cost_from_taps(src, y, x, H, W, bias, scale);
 }
 
+// Double-double accumulator for the running sums of the event-based backward (S = sum of exp(-f/sqrt(W)) over the
+// open set, D = <Gh, v>).  Over a long search S decays by many orders of magnitude (the selected cell is always the
+// LARGEST term): a plain fp64 running sum keeps an absolute error of 1e-16 x the early, large values, which becomes
+// a large relative error once S has shrunk by 1e-10 or more (cost x10, 64x64 maps).  With an error-free TwoSum the
+// pair (hi, lo) carries ~106 bits, so removed terms cancel exactly against the identical values added earlier.
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double x) {
+    const double s = __dadd_rn(hi, x);
+    const double bb = __dadd_rn(s, -hi);
+    const double err = __dadd_rn(__dadd_rn(hi, -__dadd_rn(s, -bb)), __dadd_rn(x, -bb));
+    lo = __dadd_rn(lo, err);
+    const double t = __dadd_rn(s, lo);
+    lo = __dadd_rn(lo, -__dadd_rn(t, -s));
+    hi = t;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
         }
         // backward running sums (replicated in every lane): S = sum of v over the open set, D = <Gh, v>,
         // A / B = prefix sums of 1/S and D/S^2 over the steps executed so far
-        double Ssum = 0.0, Dsum = 0.0, Acum = 0.0, Bcum = 0.0;
+        double Ssum = 0.0, Slo = 0.0, Dsum = 0.0, Dlo = 0.0, Acum = 0.0, Bcum = 0.0;   // (Ssum,Slo), (Dsum,Dlo): double-double
         auto gh_at = [&](int i) -> float { return (blocked && i == goal_idx) ? 0.f : __ldg(gG + i); };
         if (start_idx >= 0 && lane == 0) {
             const int sy = start_idx / W, sx = start_idx - sy * W;
@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
             if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
             double A1 = 0.0, B1 = 0.0;   // prefix sums INCLUDING step t (events of step t take effect from t+1 on)
             if (kBwd) {
-                const double inv = 1.0 / Ssum;
-                const double a_t = inv, b_t = Dsum * inv * inv;
+                const double inv = 1.0 / (Ssum + Slo);
+                const double a_t = inv, b_t = (Dsum + Dlo) * inv * inv;
                 const bool last = stationary_ok && (ts_in >= 0) && (t == ts_in + 1);
                 if (last) {
                     // the map is solved and re-selects its goal with a frozen open set until step T_batch-1
@@ -361,8 +361,8 @@ __global__ void __launch_bounds__(32) astar_generic_kernel(const GenArgs a) {
                 }
                 dS = __shfl_sync(kFull, dS, 0);
                 dD = __shfl_sync(kFull, dD, 0);
-                Ssum += dS;
-                Dsum += dD;
+                dd_add(Ssum, Slo, dS);
+                dd_add(Dsum, Dlo, dD);
                 Acum = A1;
                 Bcum = B1;
             }

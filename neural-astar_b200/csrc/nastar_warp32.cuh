@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
 
     // backward: running sums replicated in every lane (S = sum of v over the open set, D = <Gh, v>, A / B = prefix
     // sums of 1/S and D/S^2 over the executed steps)
-    double Ssum = 0.0, Dsum = 0.0, Acum = 0.0, Bcum = 0.0;
+    double Ssum = 0.0, Slo = 0.0, Dsum = 0.0, Dlo = 0.0, Acum = 0.0, Bcum = 0.0;   // (Ssum,Slo), (Dsum,Dlo): double-double
     int Tb = 0, ts_in = NASTAR_TS_CAPPED;
     if (kBwd) {
         Tb = *a.T_batch;
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
         double A1 = 0.0, B1 = 0.0;   // prefix sums INCLUDING step t (the events of step t act from t+1 on)
         if (kBwd) {
-            const double inv = 1.0 / Ssum;
-            const double a_t = inv, b_t = Dsum * inv * inv;
+            const double inv = 1.0 / (Ssum + Slo);
+            const double a_t = inv, b_t = (Dsum + Dlo) * inv * inv;
             if (stationary_ok && (ts_in >= 0) && (t == ts_in + 1)) {
                 // solved: the goal is re-selected with a frozen open set until step T_batch-1 (App. A.4)
                 Acum += double(Tb - t) * a_t;
@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
                          s2 = __shfl_sync(kFull, dS, min(r + 1, 31));
             const double d0 = __shfl_sync(kFull, dD, max(r - 1, 0)), d1 = __shfl_sync(kFull, dD, r),
                          d2 = __shfl_sync(kFull, dD, min(r + 1, 31));
-            Ssum += (r > 0 ? s0 : 0.0) + s1 + (r < 31 ? s2 : 0.0);
-            Dsum += (r > 0 ? d0 : 0.0) + d1 + (r < 31 ? d2 : 0.0);
+            dd_add(Ssum, Slo, (r > 0 ? s0 : 0.0) + s1 + (r < 31 ? s2 : 0.0));
+            dd_add(Dsum, Dlo, (r > 0 ? d0 : 0.0) + d1 + (r < 31 ? d2 : 0.0));
             Acum = A1;
             Bcum = B1;
         }

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
     S.open_row[lane] = open[0];
     S.open_row[lane + 32] = open[1];
     // backward state: running sums replicated in every lane
-    double Ssum = 0.0, Dsum = 0.0, Acum = 0.0, Bcum = 0.0;
+    double Ssum = 0.0, Slo = 0.0, Dsum = 0.0, Dlo = 0.0, Acum = 0.0, Bcum = 0.0;   // (Ssum,Slo), (Dsum,Dlo): double-double
     int Tb = 0, ts_in = NASTAR_TS_CAPPED;
     if (kBwd) {
         Tb = *a.T_batch;
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
         if (m == kKeyInf) { t_solve = NASTAR_TS_EXHAUSTED; break; }
         double A1 = 0.0, B1 = 0.0;   // prefix sums INCLUDING step t (the events of step t act from t+1 on)
         if (kBwd) {
-            const double inv = 1.0 / Ssum;
-            const double a_t = inv, b_t = Dsum * inv * inv;
+            const double inv = 1.0 / (Ssum + Slo);
+            const double a_t = inv, b_t = (Dsum + Dlo) * inv * inv;
             if (stationary_ok && (ts_in >= 0) && (t == ts_in + 1)) {
                 // solved: the goal is re-selected with a frozen open set until step T_batch-1
                 Acum += double(Tb - t) * a_t;
@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
             if (isr && !solved) event(int(ind), 0.f);                      // the selected cell leaves the open set
             // the events sit on the (at most three) lanes that own rows r-1, r, r+1
             const int l0 = (r - 1) & 31, l1 = r & 31, l2 = (r + 1) & 31;
-            Ssum += __shfl_sync(kFull, dS, l0) + __shfl_sync(kFull, dS, l1) + __shfl_sync(kFull, dS, l2);
-            Dsum += __shfl_sync(kFull, dD, l0) + __shfl_sync(kFull, dD, l1) + __shfl_sync(kFull, dD, l2);
+            dd_add(Ssum, Slo, __shfl_sync(kFull, dS, l0) + __shfl_sync(kFull, dS, l1) + __shfl_sync(kFull, dS, l2));
+            dd_add(Dsum, Dlo, __shfl_sync(kFull, dD, l0) + __shfl_sync(kFull, dD, l1) + __shfl_sync(kFull, dD, l2));
             Acum = A1;
             Bcum = B1;
         }
