@@ -272,6 +272,10 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         const uint32_t open_r = (kContinue && solved) ? S.open_row[r] : (S.open_row[r] & ~m1);
         const uint32_t krs = S.key[(r << 5) + lane];
         const uint32_t rs_key = ((open_r >> lane) & 1u) ? krs : kKeyInf;
+        // the rescan's two reductions are issued here, ahead of the expansion's ALU chain, so that their latency
+        // overlaps it instead of extending the tail of the step (their inputs are pre-step values only)
+        const uint32_t mr = __reduce_min_sync(kFull, rs_key);
+        const uint32_t mc = __reduce_min_sync(kFull, (rs_key == mr) ? uint32_t(lane) : 0xFFFFFFFFu);
         // -- expansion inputs ----------------------------------------------------------------
         const int dr = lane - r;
         const bool isr = (dr == 0);
@@ -343,8 +347,6 @@ __global__ void __launch_bounds__(32, 12) astar_warp32_kernel(const W32Args a) {
         if (!kContinue && solved) break;                    // :251-252 (per-map early exit, App. A.4)
         if (near) S.open_row[lane] = open;
         // -- fold the rescan into lane r's cached minimum -------------------------------------
-        const uint32_t mr = __reduce_min_sync(kFull, rs_key);
-        const uint32_t mc = __reduce_min_sync(kFull, (rs_key == mr) ? uint32_t(lane) : 0xFFFFFFFFu);
         const bool take = isr & ((mr < rm_key) | ((mr == rm_key) & (int(mc) < rm_col)));
         rm_key = take ? mr : rm_key;
         rm_col = take ? int(mc) : rm_col;
