@@ -405,7 +405,7 @@ def config_c3(dev, peak):
     algo = 36 * N * B    # 28*N forward + read grad_histories + write grad_cost
     ach = algo / ((fwd_us + bwd_us) * 1e-6) / 1e9
     # the same pair on 64x64 maps (the reference's all_064 set: tests/golden/all064_vanilla.npz, 12 maps x8), training
-    # cap T = 0.25*64*64: forward on the warp64 engine, backward on the generic engine's event-based closed form
+    # cap T = 0.25*64*64: forward and event-based backward on the warp64 engine
     g64 = load_problem("all064_vanilla")[3]
     rep = 8
     o64, s64, g64t = (torch.from_numpy(np.tile(x, (rep, 1, 1, 1))).to(dev) for x in (g64.obst, g64.start, g64.goal))
@@ -423,7 +423,7 @@ def config_c3(dev, peak):
             "search_fwd_us": fwd_us, "search_bwd_us": bwd_us,
             "grid64": {"workload": "search kernels alone, all_064 maps (12 distinct x8 = 96), learned-like costs, T = 1024 cap",
                        "fwd_us": f64_us, "bwd_us": b64_us, "bwd_over_fwd": b64_us / f64_us,
-                       "engines": "forward: warp64 (engine 4); backward: generic engine, event-based closed form"},
+                       "engines": "forward and backward: warp64 (engine 4), event-based closed form"},
             "roofline": {"bound": "hbm", "kernel": "astar_warp32_kernel<0,0,0> + <0,1,0>", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_launch": algo}}
 
