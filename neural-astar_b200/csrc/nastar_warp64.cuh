@@ -251,9 +251,6 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
             const uint32_t kb2 = ((open_r >> (lane + 32)) & 1ull) ? kb : kKeyInf;
             if (kb2 < rs_key) { rs_key = kb2; rs_col = lane + 32; }
         }
-        // issued ahead of the expansion so that the two reductions overlap its ALU chain (pre-step inputs only)
-        const uint32_t mr = __reduce_min_sync(kFull, rs_key);
-        const uint32_t mc = __reduce_min_sync(kFull, (rs_key == mr) ? uint32_t(rs_col) : 0xFFFFFFFFu);
         // which of this lane's rows (if any) is in r-1..r+1
         const int d0 = lane - r, d1 = lane + 32 - r;
         const bool near1 = (unsigned(d1 + 1) <= 2u);
@@ -329,6 +326,10 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
         if (solved && t_solve < 0) t_solve = t;
         if (!kContinue && solved) break;
         // fold the rescan into the cached minimum of row r (lane r&31, slot r>>5)
+        // (kept AFTER the expansion: hoisting these two reductions above it, as the warp32 engine does, lands them inside
+        // the divergent region of the `near` lanes here and REDUX then takes its slow divergent path — 3.6x slower)
+        const uint32_t mr = __reduce_min_sync(kFull, rs_key);
+        const uint32_t mc = __reduce_min_sync(kFull, (rs_key == mr) ? uint32_t(rs_col) : 0xFFFFFFFFu);
         if (lane == (r & 31)) {
             if (r >> 5) {
                 if ((mr < rm_key[1]) | ((mr == rm_key[1]) & (int(mc) < rm_col[1]))) { rm_key[1] = mr; rm_col[1] = int(mc); }
