@@ -344,6 +344,21 @@ def test_tf32_encoder_mask_differences_are_counted():
     assert res[False]["maps_hist_differ"] <= 15 and res[True]["maps_hist_differ"] <= 60
 
 
+def test_warp64_engine_on_the_whole_all064_test_split(native, oracle):
+    """All 400 test problems of the reference's 64x64 dataset (all_064_moore_c16) through the warp-resident 64-wide
+    engine: histories / paths bit-exact against the reference's own VanillaAstar outputs
+    (tests/golden/inputs_all064_test400.npz); the CPU oracle is pinned to the same vectors on a sample."""
+    g = Golden("inputs_all064_test400")
+    c, s, gl = _cu(g.obst), _cu(g.start), _cu(g.goal)
+    hist, paths, ts, ns, _ = native.forward(c, s, gl, c, 0.5, 64 * 64)
+    np.testing.assert_array_equal(hist.cpu().numpy() != 0, g.bits("hist_bits") != 0)
+    np.testing.assert_array_equal(paths.cpu().numpy() != 0, g.bits("path_bits") != 0)
+    np.testing.assert_array_equal(ns.cpu().numpy(), g.z["hist_sum"])
+    sl = slice(0, 400, 40)
+    ref = oracle.forward(g.obst[sl], g.start[sl], g.goal[sl], g.obst[sl], mode="literal")
+    np.testing.assert_array_equal(ref.histories != 0, g.bits("hist_bits")[sl] != 0)
+
+
 def test_end_to_end_masks_on_all_1000_maps():
     """System-level parity on the whole mazes_032 dataset (800 train + 100 valid + 100 test problems): NeuralAstar
     with the shipped checkpoint through the engine's fused forward vs the masks the REFERENCE produced for the same
