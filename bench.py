@@ -379,6 +379,19 @@ def config_c3(dev, peak):
         step()
     b.record()
     torch.cuda.synchronize()
+    ms_eager = a.elapsed_time(b) / K
+    # the same step as ONE CUDA-graph launch (neural_astar.utils.training.GraphedTrainStep)
+    from neural_astar.utils.training import GraphedTrainStep
+
+    gstep = GraphedTrainStep(module, batch)
+    for _ in range(3):
+        gstep(batch)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(K):
+        gstep(batch)
+    b.record()
+    torch.cuda.synchronize()
     ms = a.elapsed_time(b) / K
     # the two search kernels alone: forward (T = 256 cap) and closed-form backward, on the current cost maps
     with torch.no_grad():
@@ -419,7 +432,9 @@ def config_c3(dev, peak):
     bw64 = lambda: _native.backward(c64, s64, g64t, o64, gh64, Tb64, ts64, 0.5)  # noqa: E731
     f64_us, b64_us = t_of(fw64), t_of(bw64)
     return {"workload": "NeuralAstar training step (Tmax=0.25 -> T=256, b=100, RMSprop, L1), mazes_032 first train batch",
-            "train_steps_per_s": 1e3 / ms, "maps_per_s": B * 1e3 / ms, "ms_per_step": ms,
+            "train_steps_per_s": 1e3 / ms, "maps_per_s": B * 1e3 / ms, "ms_per_step": ms, "ms_per_step_eager": ms_eager,
+            "api": "neural_astar.utils.training.GraphedTrainStep (forward + L1 loss + backward + RMSprop as one CUDA graph); "
+                   "ms_per_step_eager = the same step issued op by op from Python",
             "search_fwd_us": fwd_us, "search_bwd_us": bwd_us,
             "grid64": {"workload": "search kernels alone, all_064 maps (12 distinct x8 = 96), learned-like costs, T = 1024 cap",
                        "fwd_us": f64_us, "bwd_us": b64_us, "bwd_over_fwd": b64_us / f64_us,

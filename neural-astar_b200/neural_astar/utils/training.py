@@ -72,6 +72,79 @@ def planner_metrics_from_counts(n_closed: torch.Tensor, path_len: torch.Tensor):
     return vals[0], vals[1], vals[2]
 
 
+class GraphedTrainStep:
+    """One training step of scripts/train.py (forward, L1 loss on histories, backward through the search kernels
+    and the encoder, RMSprop update; reference utils/training.py:52-61) captured ONCE as a CUDA graph and replayed.
+
+    An eager step issues ~150 small launches from Python (train-mode convs + BatchNorms, their backward, the two
+    search kernels, the optimiser's foreach kernels) and is CPU-launch bound at b=100 / 32x32; the replay is one
+    launch.  Same arithmetic as the eager step (same kernels, same order).  Fixed batch shape; `g_ratio >= 0.5` or
+    batch 1 (the batch-coupled procedure below 0.5 needs a host decision per batch).
+
+        step = GraphedTrainStep(module, example_batch)        # module: PlannerModule, in train() mode, on CUDA
+        for batch in loader:
+            loss = step(batch)                                # device scalar; float(loss) synchronises
+    """
+
+    def __init__(self, module, example_batch, warmup: int = 3):
+        planner = module.planner
+        if not module.training:
+            raise ValueError("GraphedTrainStep captures the training step: call module.train() first")
+        if float(getattr(planner, "g_ratio", 0.5)) < 0.5 and example_batch[0].shape[0] > 1:
+            raise ValueError("g_ratio < 0.5 needs a host decision per batch and cannot be captured")
+        self.module = module
+        dev = next(planner.parameters()).device
+        self.optimizer = torch.optim.RMSprop(planner.parameters(), module.config.params.lr, capturable=True)
+        self._batch = [torch.empty(x.shape, dtype=x.dtype, device=dev) for x in example_batch]
+        for dst, src in zip(self._batch, example_batch):
+            dst.copy_(torch.as_tensor(src))
+        # warm-up on a side stream (cuDNN autotuning, lazy initialisation, optimiser state), then capture; the
+        # parameters are restored afterwards so that constructing the step does not train the model
+        saved = [p.detach().clone() for p in planner.parameters()]
+        bufs = [b.detach().clone() for b in planner.buffers()]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._one_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._loss = self._one_step(zero=False)
+        with torch.no_grad():
+            for p, q in zip(planner.parameters(), saved):
+                p.copy_(q)
+            for b, q in zip(planner.buffers(), bufs):
+                b.copy_(q)
+        self.optimizer = self._reset_optimizer_state()
+        self.replays = 0
+
+    def _one_step(self, zero: bool = True):
+        if zero:
+            self.optimizer.zero_grad(set_to_none=True)
+        loss, _ = self.module._loss(self._batch)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def _reset_optimizer_state(self):
+        # the captured graph updates the optimiser state tensors in place: zero them instead of replacing them
+        for st in self.optimizer.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()
+        return self.optimizer
+
+    def __call__(self, batch) -> torch.Tensor:
+        for dst, src in zip(self._batch, batch):
+            dst.copy_(torch.as_tensor(src), non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        return self._loss
+
+
 class PlannerModule(_ModuleBase):
     def __init__(self, planner, config):
         super().__init__()

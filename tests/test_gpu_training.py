@@ -68,6 +68,48 @@ def test_training_curve_matches_reference():
     assert final_abs == pytest.approx(float(z["final_abs"]), rel=1e-3)
 
 
+def test_graphed_train_step_matches_eager():
+    """utils/training.GraphedTrainStep replays the whole training step (forward, L1 loss, search + encoder backward,
+    RMSprop) as one CUDA graph: same losses and parameters as the eager loop from the same initialisation, and
+    constructing it does not change the model."""
+    from types import SimpleNamespace
+
+    from neural_astar.planner import NeuralAstar
+    from neural_astar.utils.training import GraphedTrainStep, PlannerModule
+
+    z, maps, starts, goals, opts = _batch()
+    batch = [torch.from_numpy(x).cuda() for x in (maps, starts, goals, opts)]
+
+    def make():
+        torch.manual_seed(1234)
+        planner = NeuralAstar(encoder_input="m+", encoder_arch="CNN", encoder_depth=4, Tmax=0.25)
+        return PlannerModule(planner, SimpleNamespace(params=SimpleNamespace(lr=1e-3))).cuda().train()
+
+    eager = make()
+    opt = eager.configure_optimizers()
+    eager_losses = []
+    for step in range(3):
+        opt.zero_grad()
+        loss = eager.training_step(batch, step)
+        loss.backward()
+        opt.step()
+        eager_losses.append(float(loss))
+
+    graphed = make()
+    before = float(sum(p.detach().abs().sum() for p in graphed.planner.parameters()))
+    step_fn = GraphedTrainStep(graphed, batch)
+    after = float(sum(p.detach().abs().sum() for p in graphed.planner.parameters()))
+    assert after == before, "constructing the graphed step must leave the parameters untouched"
+    graph_losses = [float(step_fn(batch)) for _ in range(3)]
+    assert step_fn.replays == 3
+    np.testing.assert_allclose(graph_losses, eager_losses, rtol=2e-3)
+    pe = float(sum(p.detach().abs().sum() for p in eager.planner.parameters()))
+    pg = float(sum(p.detach().abs().sum() for p in graphed.planner.parameters()))
+    assert pg == pytest.approx(pe, rel=1e-3)
+    # and the curve is the reference's (tests/golden/train_curve_mazes032.npz, fp32 convs there: 2 % like above)
+    np.testing.assert_allclose(graph_losses, z["losses"][:3], rtol=3e-2)
+
+
 def test_validation_metrics_on_device():
     """validation_step logs p_opt / p_exp / h_mean (utils/training.py:63-87) without leaving the GPU."""
     from types import SimpleNamespace
