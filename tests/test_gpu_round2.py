@@ -362,28 +362,41 @@ def test_warp64_engine_on_the_whole_all064_test_split(native, oracle):
 def test_end_to_end_masks_on_all_1000_maps():
     """System-level parity on the whole mazes_032 dataset (800 train + 100 valid + 100 test problems): NeuralAstar
     with the shipped checkpoint through the engine's fused forward vs the masks the REFERENCE produced for the same
-    inputs on CPU (tests/golden/inputs_mazes032_all1000.npz).  The cuDNN encoder (TF32 convs) perturbs costs at the
-    1e-4 level, so a handful of near-tie selections may flip: the count is recorded and bounded at 1 % of the maps."""
+    inputs on CPU (tests/golden/inputs_mazes032_all1000.npz).  The search itself is bit-exact; what can differ is the
+    cost map: the cuDNN encoder's TF32 convolutions perturb costs at the 5e-4 level (fp32 convs: 1e-6), which flips a
+    near-tie selection in a few maps.  Both settings are counted, recorded and bounded (first measurement: TF32
+    9 / 1000 maps differ in histories, 5 in paths)."""
     import json
+
+    import neural_astar.planner.encoder as enc
 
     g = Golden("inputs_mazes032_all1000")
     na = _ckpt_planner()
     ref_h, ref_p = g.bits("neural_hist_bits") != 0, g.bits("neural_path_bits") != 0
     maps, start, goal = (_cu(x) for x in (g.obst, g.start, g.goal))
-    dh = dp = 0
-    with torch.no_grad():
-        for i in range(0, 1000, 100):
-            out = na(maps[i:i + 100], start[i:i + 100], goal[i:i + 100])
-            h, p = out.histories.cpu().numpy() != 0, out.paths.cpu().numpy() != 0
-            dh += int((h != ref_h[i:i + 100]).reshape(100, -1).any(1).sum())
-            dp += int((p != ref_p[i:i + 100]).reshape(100, -1).any(1).sum())
-    print(f"end-to-end vs reference on 1000 maps: {dh} maps differ in histories, {dp} in paths")
+    res = {}
+    old = enc.ALLOW_TF32
+    try:
+        for tf32 in (True, False):
+            enc.ALLOW_TF32 = tf32
+            dh = dp = 0
+            with torch.no_grad():
+                for i in range(0, 1000, 100):
+                    out = na(maps[i:i + 100], start[i:i + 100], goal[i:i + 100])
+                    h, p = out.histories.cpu().numpy() != 0, out.paths.cpu().numpy() != 0
+                    dh += int((h != ref_h[i:i + 100]).reshape(100, -1).any(1).sum())
+                    dp += int((p != ref_p[i:i + 100]).reshape(100, -1).any(1).sum())
+            res["tf32" if tf32 else "fp32"] = {"maps": 1000, "maps_hist_differ": dh, "maps_path_differ": dp}
+    finally:
+        enc.ALLOW_TF32 = old
+    print("end-to-end vs reference on 1000 maps:", res)
     try:
         with open(os.path.join(ROOT, "gpurun_out", "r02_e2e_mask_diff_1000.json"), "w") as f:
-            json.dump({"maps": 1000, "maps_hist_differ": dh, "maps_path_differ": dp}, f)
+            json.dump(res, f, indent=1)
     except OSError:
         pass
-    assert dh <= 10 and dp <= 10
+    assert res["fp32"]["maps_hist_differ"] <= 10 and res["fp32"]["maps_path_differ"] <= 10
+    assert res["tf32"]["maps_hist_differ"] <= 40 and res["tf32"]["maps_path_differ"] <= 40
 
 
 # ------------------------------------------------------------------------------------------------ graphs / pipeline
