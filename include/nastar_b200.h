@@ -174,6 +174,16 @@ int nastar_b200_pack_inputs(const float *map_designs, int32_t C, int32_t Hm, int
 int nastar_b200_cost_from_taps(const float *taps, int32_t B, int32_t H, int32_t W, float bias, float scale,
                                float *cost, void *stream);
 
+/* First encoder layer of the "m+" planners fused with the input assembly (astar.py:172-177 + the first
+ * Conv2d(2,32,3,padding=1) + BatchNorm + ReLU of encoder.py:60-78): out[b][y][x][0..31] (channels-last fp32) =
+ * relu(bias + conv3x3(cat(map_designs, start + goal))).  map_designs: fp32 [B][H*W] contiguous (one channel);
+ * start / goal: [B][H*W] planes with element strides; w_host: HOST pointer, fp32 [9 taps][2 in][32 out] with
+ * BatchNorm folded in; bias_host: HOST pointer, fp32 [32] (both copied into the launch's parameter block, i.e. the
+ * constant bank — safe to capture in a CUDA graph).  Same spatial size for maps and marks only; B*H*W <= 2^30. */
+int nastar_b200_conv1_marks(const float *map_designs, const float *start, int64_t start_stride, const float *goal,
+                            int64_t goal_stride, int32_t B, int32_t H, int32_t W, const float *w_host,
+                            const float *bias_host, float *out, void *stream);
+
 /* Head of the encoder (its last 3x3 conv has ONE output channel, encoder.py:60-78): taps[p][k] = sum_c x[p][c] *
  * w[c][k] for every pixel p of the channels-last activation x (fp32 [P][C], C in {32,64,128,256}), k = ky*3+kx.
  * `w` is a HOST pointer to C*9 floats ([c][k], BatchNorm folded): it is passed to the kernel by value (constant

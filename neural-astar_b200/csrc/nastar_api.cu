@@ -5,6 +5,7 @@
 #include <cstdio>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/nastar_b200.h"
 #include "nastar_bin16.cuh"
@@ -448,6 +449,27 @@ int nastar_b200_cost_from_taps(const float* taps, int32_t B, int32_t H, int32_t 
     const int64_t want = (total + 255) / 256;
     const int grid = int(want < int64_t(num_sms()) * 16 ? want : int64_t(num_sms()) * 16);
     nastar::cost_from_taps_kernel<<<grid, 256, 0, stream>>>(taps, B, H, W, bias, scale, cost);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e);
+    return NASTAR_OK;
+}
+
+int nastar_b200_conv1_marks(const float* map_designs, const float* start, int64_t start_stride, const float* goal,
+                            int64_t goal_stride, int32_t B, int32_t H, int32_t W, const float* w_host,
+                            const float* bias_host, float* out, void* stream_v) {
+    if (!map_designs || !start || !goal || !w_host || !bias_host || !out || B <= 0 || H <= 0 || W <= 0) return NASTAR_EINVAL;
+    if (reinterpret_cast<uintptr_t>(out) & 15) return NASTAR_EINVAL;
+    const int64_t n_pix = int64_t(B) * H * W;
+    if (n_pix > (int64_t(1) << 30)) return NASTAR_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    nastar::Conv1Weights cw;
+    std::memcpy(cw.w, w_host, sizeof(cw.w));
+    std::memcpy(cw.b, bias_host, sizeof(cw.b));
+    const int64_t want = (n_pix + 32 * nastar::kConv1Warps - 1) / (32 * nastar::kConv1Warps);
+    const int grid = int(want < int64_t(num_sms()) * 8 ? want : int64_t(num_sms()) * 8);
+    nastar::conv1_marks_kernel<<<grid, 32 * nastar::kConv1Warps, 0, stream>>>(map_designs, start, start_stride, goal,
+                                                                             goal_stride, int(n_pix), H, W, cw, out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e);

@@ -55,6 +55,77 @@ __global__ void __launch_bounds__(256) cost_from_taps_kernel(const float* __rest
     }
 }
 
+// ---- first encoder layer fused with the input assembly ("m+" planners) --------------------------------------------
+// conv1 of the CNN encoder has 2 input channels (the map and the start+goal marks, astar.py:172-177) and 32 output
+// channels (encoder.py:60-78): 18 multiply-adds per output value — not a contraction worth a tensor core, and cuDNN
+// runs it with a generic 14.6 us kernel on top of the 4.7 us pack kernel.  Here one thread owns one pixel: the marks
+// channel is formed on the fly (start + goal), the 3x3 / pad 1 window is read straight from the three input planes
+// (27 predicated loads, L1-resident: 4 KB per map and plane), the 576 FMAs take their weights from the constant bank
+// (the folded weights are a by-value kernel parameter, like the head's), BatchNorm arrives folded into w / b, ReLU is
+// applied, and the warp's 32 pixels x 32 channels are transposed through shared memory so the channels-last result
+// ([B][H][W][32]) leaves as fully coalesced 128-bit stores.  (A first version with thread = (pixel, 4 channels) and the
+// weights in shared memory was load/store-unit bound at 20 us: 8x the window loads and 18 LDS.128 per thread.)
+struct Conv1Weights {
+    float w[9][2][32];   // [tap][cin][cout], BatchNorm folded
+    float b[32];
+};
+
+constexpr int kConv1Warps = 8;
+constexpr int kConv1Row = 36;   // floats per staged pixel: 32 channels + 4 pad (keeps 16 B alignment, conflict-free quarter-warps)
+
+__global__ void __launch_bounds__(32 * kConv1Warps) conv1_marks_kernel(const float* __restrict__ maps,
+                                                                       const float* __restrict__ start, int64_t start_stride,
+                                                                       const float* __restrict__ goal, int64_t goal_stride,
+                                                                       int n_pix, int H, int W,
+                                                                       const __grid_constant__ Conv1Weights cw,
+                                                                       float* __restrict__ out) {
+    __shared__ __align__(16) float sT[kConv1Warps][32 * kConv1Row];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = H * W;
+    float* st = sT[warp];
+    for (int base = (blockIdx.x * kConv1Warps + warp) * 32; base < n_pix; base += gridDim.x * kConv1Warps * 32) {
+        const int pix = base + lane;
+        const bool live = pix < n_pix;
+        const int pc = live ? pix : 0;
+        const int b = pc / N;
+        const int rc = pc - b * N;
+        const int y = rc / W, x = rc - y * W;
+        const float* pm = maps + int64_t(b) * N;
+        const float* ps = start + int64_t(b) * start_stride;
+        const float* pg = goal + int64_t(b) * goal_stride;
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = cw.b[c];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = y + ky - 1;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = x + kx - 1;
+                const bool in = live && unsigned(yy) < unsigned(H) && unsigned(xx) < unsigned(W);
+                const int o = in ? yy * W + xx : 0;
+                const float m = in ? __ldg(pm + o) : 0.f;
+                const float k = in ? __fadd_rn(__ldg(ps + o), __ldg(pg + o)) : 0.f;   // start_maps + goal_maps (:173)
+#pragma unroll
+                for (int c = 0; c < 32; ++c) acc[c] = fmaf(k, cw.w[ky * 3 + kx][1][c], fmaf(m, cw.w[ky * 3 + kx][0][c], acc[c]));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(st + lane * kConv1Row + c) =
+                make_float4(fmaxf(acc[c], 0.f), fmaxf(acc[c + 1], 0.f), fmaxf(acc[c + 2], 0.f), fmaxf(acc[c + 3], 0.f));
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(out) + int64_t(base) * 8;     // 8 float4 per pixel
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int v = j * 32 + lane;                                       // float4 index inside the warp's 4 KB tile
+            if (base + (v >> 3) < n_pix)
+                dst[v] = *reinterpret_cast<const float4*>(st + (v >> 3) * kConv1Row + (v & 7) * 4);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- single-output-channel head of the encoder: per-pixel partial products ---------------------------------------
 // The encoder's last layer is a 3x3 conv with ONE output channel (encoder.py:60-78, channels [...,256,1]).  Round 1
 // already evaluated it as a per-pixel [C] x [C,9] product followed by a 9-tap gather (planner/encoder.py

@@ -73,6 +73,7 @@ EXPORTS = (
     "nastar_b200_pack_inputs",
     "nastar_b200_cost_from_taps",
     "nastar_b200_head_taps",
+    "nastar_b200_conv1_marks",
     "nastar_b200_selftest_sqrt",
     "nastar_b200_launch_count",
     "nastar_b200_status_string",
@@ -126,6 +127,10 @@ def lib():
     L.nastar_b200_head_taps.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p]
     L.nastar_b200_head_taps.restype = ctypes.c_int
+    L.nastar_b200_conv1_marks.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+    L.nastar_b200_conv1_marks.restype = ctypes.c_int
     L.nastar_b200_selftest_sqrt.argtypes = [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     L.nastar_b200_selftest_sqrt.restype = ctypes.c_int
     L.nastar_b200_launch_count.restype = ctypes.c_uint64
@@ -274,6 +279,33 @@ def pack_inputs(map_designs: torch.Tensor, start: torch.Tensor, goal: torch.Tens
 
 
 HEAD_CHANNELS = (32, 64, 128, 256)
+
+
+def conv1_marks(map_designs: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, w_host, bias_host) -> torch.Tensor:
+    """relu(bias + conv3x3(cat(map_designs, start + goal))) as a channels-last [B,32,H,W] tensor in one kernel (the
+    "m+" encoder's first layer fused with NeuralAstar.encode's input assembly).  w_host: C-contiguous float32 NumPy
+    array [9,2,32] = [tap, cin, cout] (BatchNorm folded), bias_host: float32 NumPy [32]; both on the HOST (they travel
+    as kernel parameters)."""
+    L = lib()
+    B, C, H, W = map_designs.shape
+    if C != 1 or start.shape[-2:] != (H, W) or map_designs.dtype != torch.float32 or not map_designs.is_cuda:
+        raise ValueError("conv1_marks: one-channel fp32 CUDA maps with start/goal maps of the same size")
+    if (w_host.dtype.name != "float32" or w_host.shape != (9, 2, 32) or not w_host.flags["C_CONTIGUOUS"]
+            or bias_host.dtype.name != "float32" or bias_host.shape != (32,) or not bias_host.flags["C_CONTIGUOUS"]):
+        raise ValueError("conv1_marks: w_host must be a C-contiguous float32 [9,2,32] array, bias_host float32 [32]")
+    md = map_designs.detach().contiguous()
+    ks, ps, ss = _plane(start.detach())
+    kg, pg, sg = _plane(goal.detach())
+    dev = map_designs.device
+    guard = contextlib.nullcontext() if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+    with guard:
+        out = torch.empty((B, H, W, 32), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(L.nastar_b200_conv1_marks(md.data_ptr(), ps, ss, pg, sg, B, H, W, w_host.ctypes.data,
+                                         bias_host.ctypes.data, out.data_ptr(), ctypes.c_void_p(stream)),
+               "nastar_b200_conv1_marks")
+    del ks, kg
+    return out.permute(0, 3, 1, 2)
 
 
 def head_taps(x: torch.Tensor, w_host, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -83,6 +83,11 @@ class NeuralAstar(VanillaAstar):
     def encode(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor) -> torch.Tensor:
         """Cost maps from the encoder; with a "+" input the start/goal marks ride along as an extra channel,
         nearest-upsampled when the image is larger than the planning grid (reference :154-180)."""
+        if ("+" in self.encoder_input and self.encoder.fast_path_ok(map_designs) and start_maps.is_cuda
+                and start_maps.dtype == torch.float32):
+            head = self.encoder.head_taps_marks(map_designs, start_maps, goal_maps)   # same kernels as forward()
+            if head is not None:
+                return _native.cost_from_taps(*head)
         return self.encoder(self._encoder_input(map_designs, start_maps, goal_maps))
 
     def _encoder_input(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor) -> torch.Tensor:
@@ -95,6 +100,15 @@ class NeuralAstar(VanillaAstar):
                 marks = F.interpolate(marks, size=x.shape[-2:], mode="nearest")
             x = torch.cat((x, marks), dim=1)
         return x
+
+    def _head_taps(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor, out=None):
+        """Encoder up to the 9-tap products of its head (EncoderBase.head_taps), from the un-assembled inputs: the
+        "m+" CNN reads the three planes in its first layer's kernel, everything else packs them first."""
+        if "+" in self.encoder_input and start_maps.is_cuda and start_maps.dtype == torch.float32:
+            head = self.encoder.head_taps_marks(map_designs, start_maps, goal_maps, out=out)
+            if head is not None:
+                return head
+        return self.encoder.head_taps(self._encoder_input(map_designs, start_maps, goal_maps), out=out)
 
     def forward(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor,
                 store_intermediate_results: bool = False) -> AstarOutput:
@@ -122,7 +136,7 @@ class NeuralAstar(VanillaAstar):
         kw = {}
         cost = None
         if H <= 32 and W <= 32 and self.encoder.fast_path_ok(map_designs):
-            head = self.encoder.head_taps(self._encoder_input(map_designs, start_maps, goal_maps))
+            head = self._head_taps(map_designs, start_maps, goal_maps)
             if head is not None:
                 cost, bias, scale = head
                 kw = dict(cost_kind=_native.COST_TAPS, cost_bias=bias, cost_scale=scale)
@@ -142,7 +156,7 @@ class NeuralAstar(VanillaAstar):
                 or not start_maps.is_cuda or (float(self.g_ratio) < 0.5 and start_maps.shape[0] > 1)
                 or start_maps.dtype != torch.float32 or passable.dtype != torch.float32):
             return None
-        head = self.encoder.head_taps(self._encoder_input(map_designs, start_maps, goal_maps))
+        head = self._head_taps(map_designs, start_maps, goal_maps)
         if head is None or head[0].shape[1:3] != (H, W):
             return None
         taps, bias, scale = head

@@ -22,6 +22,10 @@ ALLOW_TF32 = os.environ.get("NASTAR_B200_ENCODER_TF32", "1") != "0"
 # FMA, weights in the constant bank) or, with NASTAR_B200_HEAD_KERNEL=0, torch.mm (cuBLAS SGEMM, 3-4x slower on this
 # skinny shape).  Same sums up to fp32 re-association.
 HEAD_KERNEL = os.environ.get("NASTAR_B200_HEAD_KERNEL", "1") != "0"
+# First layer of the "m+" CNN (2 -> 32 channels, 18 multiply-adds per output): the engine's kernel that also forms the
+# start+goal channel and the concat on the fly (csrc/nastar_glue.cuh conv1_marks_kernel, fp32 FMA), or, with
+# NASTAR_B200_CONV1_KERNEL=0, the pack_inputs kernel followed by cuDNN's (also fp32, generic NHWC) convolution.
+CONV1_KERNEL = os.environ.get("NASTAR_B200_CONV1_KERNEL", "1") != "0"
 
 
 class EncoderBase(nn.Module):
@@ -35,6 +39,7 @@ class EncoderBase(nn.Module):
         self._nhwc = False      # conv weights converted to channels-last (done lazily on the first CUDA batch)
         self._head_scalars = (0.0, 1.0)   # (folded bias of the head conv, const) as Python floats
         self._head_w_host = None          # folded [C,9] weights of the head conv on the host (kernel parameter)
+        self._conv1 = None                # folded ([9,2,32] weights, [32] bias) of a 2->32 first layer, NumPy on the host
 
     def construct_encoder(self, input_dim: int, encoder_depth: int) -> nn.Module:
         raise NotImplementedError
@@ -78,8 +83,27 @@ class EncoderBase(nn.Module):
         if plan is None or plan[-1][7] is None:
             return None
         x = x.contiguous(memory_format=torch.channels_last)
+        return self._head_from(plan, 0, x, out)
+
+    def head_taps_marks(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor,
+                        out: Optional[torch.Tensor] = None):
+        """head_taps() of the "m+" input cat(map_designs, start_maps + goal_maps) without materialising it: the first
+        layer reads the three planes directly (one kernel instead of pack_inputs + cuDNN's conv1).  None when the
+        encoder's first layer is not the 2->32 3x3/ReLU block, the maps are not one-channel or the marks live on a
+        different grid; callers then pack the input and use head_taps()."""
+        if not CONV1_KERNEL or map_designs.shape[1] != 1 or map_designs.shape[-2:] != start_maps.shape[-2:]:
+            return None
+        plan = self._inference_plan(map_designs.device)
+        if plan is None or plan[-1][7] is None or self._conv1 is None or len(plan) < 2:
+            return None
+        from .. import _native
+
+        x = _native.conv1_marks(map_designs, start_maps, goal_maps, self._conv1[0], self._conv1[1])
+        return self._head_from(plan, 1, x, out)
+
+    def _head_from(self, plan, first: int, x: torch.Tensor, out: Optional[torch.Tensor]):
         with _conv_flags():
-            x = _run_plan_inner(plan[:-1], x)
+            x = _run_plan_inner(plan[first:-1], x)
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
         wm = plan[-1][7][0]
@@ -144,6 +168,13 @@ class EncoderBase(nn.Module):
                               float(self.const) if not isinstance(self.const, float) else self.const)
         head = plan[-1][7]
         self._head_w_host = head[0].detach().cpu().numpy().astype("float32", order="C") if head is not None else None
+        w0, b0, st0, pad0, dil0, relu0, pool0, head0 = plan[0]
+        self._conv1 = None
+        if (tuple(w0.shape) == (32, 2, 3, 3) and tuple(st0) == (1, 1) and tuple(pad0) == (1, 1) and tuple(dil0) == (1, 1)
+                and relu0 and pool0 is None and head0 is None and w0.is_cuda and w0.dtype == torch.float32):
+            with torch.no_grad():       # [cout, cin, ky, kx] -> [tap, cin, cout]
+                self._conv1 = (w0.permute(2, 3, 1, 0).reshape(9, 2, 32).cpu().numpy().astype("float32", order="C"),
+                               b0.detach().cpu().numpy().astype("float32", order="C"))
         self._plan, self._plan_key = plan, key
         return plan
 

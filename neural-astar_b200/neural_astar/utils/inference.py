@@ -194,7 +194,7 @@ class PipelinedPlanner:
     # -- building blocks ---------------------------------------------------------------------------------
     def _encode(self, ins, out=None):
         p = self.planner
-        return p.encoder.head_taps(p._encoder_input(*ins), out=out)
+        return p._head_taps(*ins, out=out)
 
     def _search(self, par):
         p = self.planner

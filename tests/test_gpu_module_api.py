@@ -204,7 +204,7 @@ def test_graphed_planner_matches_eager():
     with torch.no_grad():
         want = na(maps, start, goal)
     fast = GraphedPlanner(na, maps, start, goal)
-    assert fast.native_launches_per_replay == 3     # pack_inputs + head products + the search kernel (TAPS prologue); the rest is cuDNN
+    assert fast.native_launches_per_replay == 3     # first layer + head products + the search kernel (TAPS prologue); the rest is cuDNN
     # a different batch of the same shape through the captured graph
     perm = torch.randperm(maps.shape[0], device="cuda")
     with torch.no_grad():

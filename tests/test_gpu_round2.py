@@ -250,6 +250,60 @@ def test_head_taps_kernel_matches_fp32_matmul(native, C, B, H):
     assert native.head_taps(x, w.cpu().numpy(), out=buf).data_ptr() == buf.data_ptr() and torch.equal(buf, got)
 
 
+@pytest.mark.parametrize("B,H,W", [(7, 32, 32), (3, 20, 27), (2, 64, 64), (1, 5, 3)])
+def test_conv1_marks_matches_torch_conv(native, B, H, W):
+    """First encoder layer fused with the input assembly vs torch: relu(conv2d(cat(map, start + goal), w, b)) in fp32
+    (different summation order only), channels-last result."""
+    torch.manual_seed(B * H + W)
+    maps = (torch.rand(B, 1, H, W, device="cuda") > 0.2).float()
+    start = torch.zeros(B, 1, H, W, device="cuda")
+    goal = torch.zeros_like(start)
+    for b in range(B):
+        start[b, 0, b % H, (3 * b) % W] = 1
+        goal[b, 0, H - 1 - b % H, W - 1] = 1
+    w = torch.randn(32, 2, 3, 3, device="cuda") * 0.3
+    bias = torch.randn(32, device="cuda") * 0.1
+    want = torch.relu(torch.nn.functional.conv2d(torch.cat((maps, start + goal), 1).double(), w.double(), bias.double(),
+                                                 padding=1))
+    wh = np.ascontiguousarray(w.permute(2, 3, 1, 0).reshape(9, 2, 32).cpu().numpy())
+    bh = bias.cpu().numpy()
+    got = native.conv1_marks(maps, start, goal, wh, bh)
+    assert got.shape == (B, 32, H, W) and got.is_contiguous(memory_format=torch.channels_last)
+    assert float((got.double() - want).abs().max()) < 1e-5
+    # strided one-hot planes (views into a stacked request buffer) are read in place
+    stacked = torch.stack((maps, start, goal), 0)
+    got2 = native.conv1_marks(stacked[0], stacked[1], stacked[2], wh, bh)
+    assert torch.equal(got2, got)
+    with pytest.raises(ValueError):
+        native.conv1_marks(maps.repeat(1, 2, 1, 1), start, goal, wh, bh)
+
+
+def test_first_layer_kernel_equals_packed_cudnn_path(native, monkeypatch):
+    """NeuralAstar.forward with the engine's first-layer kernel vs the pack_inputs + cuDNN first layer (both fp32, other
+    layers identical): the 9-tap products agree to fp32 rounding and the search masks are the same on this batch."""
+    from neural_astar.planner import NeuralAstar, encoder
+
+    torch.manual_seed(3)
+    na = NeuralAstar(encoder_input="m+", encoder_arch="CNN", encoder_depth=4).cuda().eval()
+    B, H = 24, 32
+    x = (torch.rand(B, 1, H, H, device="cuda") > 0.15).float()
+    s = torch.zeros(B, 1, H, H, device="cuda"); s[:, :, 0, 0] = 1
+    g = torch.zeros_like(s); g[:, :, -1, -1] = 1
+    x[:, :, 0, 0] = 1; x[:, :, -1, -1] = 1
+    monkeypatch.setattr(encoder, "ALLOW_TF32", False)
+    with torch.no_grad():
+        assert na.encoder.head_taps_marks(x, s, g) is not None
+        t_new = na._head_taps(x, s, g)[0].clone()
+        out_new = na(x, s, g)
+        monkeypatch.setattr(encoder, "CONV1_KERNEL", False)
+        assert na.encoder.head_taps_marks(x, s, g) is None
+        t_old = na._head_taps(x, s, g)[0].clone()
+        out_old = na(x, s, g)
+    assert float((t_new - t_old).abs().max()) < 1e-4
+    assert int((out_new.histories != out_old.histories).flatten(1).any(1).sum()) <= 1
+    assert int((out_new.paths != out_old.paths).flatten(1).any(1).sum()) <= 1
+
+
 @pytest.mark.parametrize("C,Hm,H", [(1, 32, 32), (3, 96, 12), (2, 24, 12), (1, 64, 64)])
 def test_pack_inputs_matches_torch(native, C, Hm, H):
     torch.manual_seed(C + Hm)
@@ -292,7 +346,7 @@ def test_fused_forward_equals_unfused_composition(native, arch, inp, depth, cons
         na(x, s, g)             # plan building
         before = native.launch_count()
         out = na(x, s, g, store_intermediate_results=False)
-        assert native.launch_count() - before == 3          # pack_inputs + head products + search; the rest is cuDNN
+        assert native.launch_count() - before == 3          # first layer (or pack_inputs) + head products + search; the rest is cuDNN
         cost = na.encode(x, s, g)
         passable = torch.ones_like(s) if na.learn_obstacles else x
         want = na.perform_astar(cost, s, g, passable)

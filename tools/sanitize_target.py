@@ -30,5 +30,7 @@ x = torch.randn(3, 64, 12, 12, device="cuda").contiguous(memory_format=torch.cha
 _native.head_taps(x, np.ascontiguousarray(rng.randn(64, 9).astype(np.float32)))
 m = torch.rand(3, 3, 96, 96, device="cuda"); st = torch.zeros(3, 1, 12, 12, device="cuda"); st[:, :, 0, 0] = 1
 _native.pack_inputs(m, st, st)
+mm = torch.rand(3, 1, 20, 27, device="cuda"); s1 = torch.zeros_like(mm); s1[:, :, 0, 0] = 1
+_native.conv1_marks(mm, s1, s1, rng.randn(9, 2, 32).astype(np.float32), rng.randn(32).astype(np.float32))
 torch.cuda.synchronize()
 print("glue ok")
