@@ -698,7 +698,8 @@ def bench_ours(args):
             "search_kernel_us": kern_s * 1e6,
             "e2e": {"value": maps_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K,
-                    "api": "PipelinedPlanner(host=True): pinned H2D of the batch and D2H of histories+paths inside each step's graph"},
+                    "api": "PipelinedPlanner(host=True), three stages per step graph: pinned H2D(batch k) || encoder(k-1) || "
+                           "search(k-2) + D2H of histories+paths; K submits + drain inside the timed region"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "nastar::astar_warp32_kernel<0,0,0>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

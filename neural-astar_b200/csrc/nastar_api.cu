@@ -136,8 +136,9 @@ template <int C>
 cudaError_t launch_head(const float* x, int64_t P, const float* w_host, float* taps, cudaStream_t stream) {
     nastar::HeadWeights<C> hw;
     for (int i = 0; i < C * 9; ++i) hw.w[i] = w_host[i];
-    const int64_t blocks = (P + 127) / 128;
-    nastar::head_taps_kernel<C><<<unsigned(blocks), 128, 0, stream>>>(x, P, hw, taps);
+    const int64_t want = ((P + 31) / 32 + nastar::kHeadWarps - 1) / nastar::kHeadWarps;   // one 32-pixel group per warp
+    const int64_t cap = int64_t(num_sms()) * 16;
+    nastar::head_taps_kernel<C><<<unsigned(want < cap ? want : cap), 32 * nastar::kHeadWarps, 0, stream>>>(x, P, hw, taps);
     return cudaGetLastError();
 }
 }  // namespace

@@ -131,38 +131,74 @@ __global__ void __launch_bounds__(32 * kConv1Warps) conv1_marks_kernel(const flo
 // already evaluated it as a per-pixel [C] x [C,9] product followed by a 9-tap gather (planner/encoder.py
 // `_conv3x3_single_output`); the gather now lives in the search kernel's prologue (NASTAR_COST_TAPS).  The product
 // itself is 0.5 GFLOP over a 105 MB activation (b=100, 32x32, C=256): HBM-bound, and cuBLAS' skinny SGEMM reaches only
-// 1.2 TB/s on it (86 us).  Here: one thread per pixel streams its C contiguous channels with 128-bit loads and keeps
-// the 9 sums in registers; the C*9 weights arrive as a by-value kernel parameter, i.e. in the constant bank, so every
-// FFMA takes its weight operand straight from c[0x0][..] — no shared memory, no weight loads at all.
+// 1.2 TB/s on it (86 us).  Here: one thread per pixel keeps the 9 sums in registers; the C*9 weights arrive as a
+// by-value kernel parameter, i.e. in the constant bank, so every FFMA takes its weight operand straight from a uniform
+// register — no weight loads at all.  The activation is staged through shared memory: a warp copies its 32 pixels'
+// channel slice (32 x kSlice floats, contiguous 4*kSlice-byte runs) with fully coalesced 16-byte cp.async, then every
+// lane reads its own pixel's row back with conflict-free LDS.128 (row stride kSlice+4 floats).  Measured at b=100,
+// 32x32, C=256 (105 MB read, profiles/README.md): 26.5 us under ncu = 4.0 TB/s; torch.sum over the same tensor takes
+// 25 us.  Two alternatives were measured and dropped: each lane streaming its own 1 KB row straight from global memory
+// (every LDG.128 touches 32 different lines: 31 us), and a CTA-cooperative version with whole 32 KB tiles in a
+// cp.async ring and one channel slice per warp (weights per warp either as 8 separately unrolled constant-bank blocks
+// — instruction-cache thrash, 124 us — or as broadcast LDS.128 from shared memory — MIO-throttled, 37 us).
+// Same FMA order as the first version (ascending channel), so the products are bit-identical to it.
 template <int C>
 struct HeadWeights {
     float w[C * 9];   // [c][k], k = ky*3+kx, BatchNorm already folded
 };
 
+constexpr int kHeadWarps = 4;
+
 template <int C>
-__global__ void __launch_bounds__(128) head_taps_kernel(const float* __restrict__ x, int64_t P,
-                                                        const __grid_constant__ HeadWeights<C> hw,
-                                                        float* __restrict__ out) {
-    const int64_t p = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    const float4* xp = reinterpret_cast<const float4*>(x + p * C);
-    float acc[9];
+__global__ void __launch_bounds__(32 * kHeadWarps) head_taps_kernel(const float* __restrict__ x, int64_t P,
+                                                                    const __grid_constant__ HeadWeights<C> hw,
+                                                                    float* __restrict__ out) {
+    constexpr int kSlice = C < 64 ? C : 64;          // channels staged per pass
+    constexpr int kRow = kSlice + 4;                 // padded row (floats): 16 B aligned, quarter-warps hit 32 distinct banks
+    constexpr int kChunks = kSlice / 4;              // float4 per pixel and slice
+    __shared__ __align__(16) float sX[kHeadWarps][32 * kRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* st = sX[warp];
+    const uint32_t st_s = uint32_t(__cvta_generic_to_shared(st));
+    const int64_t groups = (P + 31) / 32;
+    for (int64_t grp = int64_t(blockIdx.x) * kHeadWarps + warp; grp < groups; grp += int64_t(gridDim.x) * kHeadWarps) {
+        const int64_t p0 = grp * 32;
+        float acc[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+        for (int k = 0; k < 9; ++k) acc[k] = 0.f;
 #pragma unroll
-    for (int c4 = 0; c4 < C / 4; ++c4) {
-        const float4 v = __ldg(xp + c4);
+        for (int s0 = 0; s0 < C; s0 += kSlice) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            acc[k] = fmaf(v.x, hw.w[(4 * c4 + 0) * 9 + k], acc[k]);
-            acc[k] = fmaf(v.y, hw.w[(4 * c4 + 1) * 9 + k], acc[k]);
-            acc[k] = fmaf(v.z, hw.w[(4 * c4 + 2) * 9 + k], acc[k]);
-            acc[k] = fmaf(v.w, hw.w[(4 * c4 + 3) * 9 + k], acc[k]);
+            for (int i = 0; i < kChunks; ++i) {      // 32 lanes x kChunks copies of 16 B = the 32 x kSlice tile
+                const int idx = i * 32 + lane;
+                const int px = idx / kChunks, ch = idx % kChunks;
+                int64_t p = p0 + px;
+                p = p < P ? p : P - 1;               // ragged last group: re-read the last pixel, never stored
+                const float* src = x + p * C + s0 + ch * 4;
+                const uint32_t dst = st_s + uint32_t(px * kRow + ch * 4) * 4u;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int c4 = 0; c4 < kChunks; ++c4) {
+                const float4 v = *reinterpret_cast<const float4*>(st + lane * kRow + c4 * 4);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    acc[k] = fmaf(v.x, hw.w[(s0 + 4 * c4 + 0) * 9 + k], acc[k]);
+                    acc[k] = fmaf(v.y, hw.w[(s0 + 4 * c4 + 1) * 9 + k], acc[k]);
+                    acc[k] = fmaf(v.z, hw.w[(s0 + 4 * c4 + 2) * 9 + k], acc[k]);
+                    acc[k] = fmaf(v.w, hw.w[(s0 + 4 * c4 + 3) * 9 + k], acc[k]);
+                }
+            }
+            __syncwarp();                            // all lanes done reading before the next slice overwrites the tile
+        }
+        if (p0 + lane < P) {
+            float* o = out + (p0 + lane) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) o[k] = acc[k];
         }
     }
-    float* o = out + p * 9;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) o[k] = acc[k];
 }
 
 }  // namespace nastar

@@ -101,14 +101,16 @@ class NeuralAstar(VanillaAstar):
             x = torch.cat((x, marks), dim=1)
         return x
 
-    def _head_taps(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor, out=None):
+    def _head_taps(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor, out=None,
+                   on_last_conv=None):
         """Encoder up to the 9-tap products of its head (EncoderBase.head_taps), from the un-assembled inputs: the
         "m+" CNN reads the three planes in its first layer's kernel, everything else packs them first."""
         if "+" in self.encoder_input and start_maps.is_cuda and start_maps.dtype == torch.float32:
-            head = self.encoder.head_taps_marks(map_designs, start_maps, goal_maps, out=out)
+            head = self.encoder.head_taps_marks(map_designs, start_maps, goal_maps, out=out, on_last_conv=on_last_conv)
             if head is not None:
                 return head
-        return self.encoder.head_taps(self._encoder_input(map_designs, start_maps, goal_maps), out=out)
+        return self.encoder.head_taps(self._encoder_input(map_designs, start_maps, goal_maps), out=out,
+                                      on_last_conv=on_last_conv)
 
     def forward(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor,
                 store_intermediate_results: bool = False) -> AstarOutput:

@@ -75,7 +75,7 @@ class EncoderBase(nn.Module):
             x = x.contiguous(memory_format=torch.channels_last)
         return torch.sigmoid(self.model(x)) * self.const
 
-    def head_taps(self, x: torch.Tensor, out: Optional[torch.Tensor] = None):
+    def head_taps(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, on_last_conv=None):
         """Eval fast path up to (not including) the 9-tap gather of the single-output-channel head:
         returns (taps [B,H,W,9] fp32 contiguous, folded bias, const) as (tensor, float, float), or None when the
         encoder does not end in such a head.  bias/const are cached Python floats (no host sync per call)."""
@@ -83,10 +83,10 @@ class EncoderBase(nn.Module):
         if plan is None or plan[-1][7] is None:
             return None
         x = x.contiguous(memory_format=torch.channels_last)
-        return self._head_from(plan, 0, x, out)
+        return self._head_from(plan, 0, x, out, on_last_conv)
 
     def head_taps_marks(self, map_designs: torch.Tensor, start_maps: torch.Tensor, goal_maps: torch.Tensor,
-                        out: Optional[torch.Tensor] = None):
+                        out: Optional[torch.Tensor] = None, on_last_conv=None):
         """head_taps() of the "m+" input cat(map_designs, start_maps + goal_maps) without materialising it: the first
         layer reads the three planes directly (one kernel instead of pack_inputs + cuDNN's conv1).  None when the
         encoder's first layer is not the 2->32 3x3/ReLU block, the maps are not one-channel or the marks live on a
@@ -99,11 +99,18 @@ class EncoderBase(nn.Module):
         from .. import _native
 
         x = _native.conv1_marks(map_designs, start_maps, goal_maps, self._conv1[0], self._conv1[1])
-        return self._head_from(plan, 1, x, out)
+        return self._head_from(plan, 1, x, out, on_last_conv)
 
-    def _head_from(self, plan, first: int, x: torch.Tensor, out: Optional[torch.Tensor]):
+    def _head_from(self, plan, first: int, x: torch.Tensor, out: Optional[torch.Tensor], on_last_conv=None):
+        """Layers plan[first:-1] (cuDNN) and the head's products.  `on_last_conv`, if given, is called once, after the
+        second-to-last convolution has been enqueued and before the last (widest) one: PipelinedPlanner forks the
+        previous batch's search there (see its docstring)."""
+        body = plan[first:-1]
         with _conv_flags():
-            x = _run_plan_inner(plan[first:-1], x)
+            x = _run_plan_inner(body[:-1], x)
+            if on_last_conv is not None:
+                on_last_conv()
+            x = _run_plan_inner(body[-1:], x)
         if not x.is_contiguous(memory_format=torch.channels_last):
             x = x.contiguous(memory_format=torch.channels_last)
         wm = plan[-1][7][0]

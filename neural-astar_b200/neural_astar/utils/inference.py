@@ -137,30 +137,53 @@ class GraphedPlanner:
 class PipelinedPlanner:
     """Software pipeline over consecutive batches of a NeuralAstar: while the search kernel of batch k runs on a
     hundred warps, the encoder convolutions of batch k+1 occupy the tensor cores.  Both are branches of one CUDA
-    graph (captured with a forked stream), double-buffered on inputs, encoder output and results; a step is ONE
+    graph (captured with forked streams), multi-buffered on inputs, encoder output and results; a step is ONE
     graph launch.  Outputs are identical to the eager call's (same kernels, same order per batch).
 
-    `host=True` builds the end-to-end variant: every step's graph also contains the H2D copy of that batch from
-    `host_inputs[k % 2]` (pinned) and the D2H copy of the finished batch into `host_outputs[k % 2]`.
+    Device inputs (default): two stages.  submit(batch k) runs  encoder(k) || search(k-1)  and returns the outputs of
+    batch k-1.
+
+    `host=True` builds the end-to-end variant, three stages deep: submit() number k runs
+        H2D(batch k, from the pinned `host_inputs[k % 3]`)  ||  encoder(k-1)  ||  search(k-2) -> D2H into the pinned
+        `host_outputs[k % 2]`
+    so both PCIe copies hide behind the convolutions (a 1.2 MB D2H of histories + int64 paths takes ~70 us here, the
+    H2D ~30 us; with the copies in line the step was 202 us, now 171 us).  Batch k's results are complete once
+    submit() number k+2 (or drain()) has finished.
+
+    `fork` places the search inside the step: "late" forks it right before the encoder's last, widest convolution,
+    "early" at the start of the step; default: "late" for device inputs, "early" with host=True.  Why it matters on
+    B200: cuDNN's sm_100 TF32 convolutions take 200-219 KB of the SM's 228 KB of shared memory per CTA
+    (profiles/r02_launchstats_graph.csv).  A search CTA (17.4 KB + 1 KB reserved) fits beside the last convolution's
+    CTAs (200.7 KB) but NOT beside those of the earlier layers (216-219 KB), so a search that is resident on 100 of
+    the 148 SMs keeps those layers off these SMs until its maps finish: the device step measured 182 us forked early
+    against 161 us for the encoder branch alone, and 170 us forked late — the first layers have the GPU to themselves
+    and the search (65 us) still hides behind last conv + head (110 us).  With host=True the search is followed by the
+    D2H copy, and search + copy (135 us) only fit inside the step when started early (171 vs 195 us).
     """
 
     def __init__(self, planner: torch.nn.Module, map_designs: torch.Tensor, start_maps: torch.Tensor,
-                 goal_maps: torch.Tensor, host: bool = False, warmup: int = 3):
+                 goal_maps: torch.Tensor, host: bool = False, warmup: int = 3, fork: Optional[str] = None):
         from ..planner.astar import NeuralAstar
 
         if not isinstance(planner, NeuralAstar):
             raise TypeError("PipelinedPlanner overlaps an encoder with the search: it needs a NeuralAstar")
         dev = _check_planner(planner, map_designs)
-        self.planner, self.device, self.host = planner, dev, host
+        if fork is None:
+            fork = "early" if host else "late"
+        if fork not in ("late", "early"):
+            raise ValueError("fork must be 'late' or 'early'")
+        self.planner, self.device, self.host, self.fork = planner, dev, host, fork
         examples = (map_designs, start_maps, goal_maps)
+        n_in = 3 if host else 2      # input buffers: H2D(k) || encoder(k-1) || search(k-2) touch three different batches
         # when the three inputs share shape and dtype (the "m+" planners) they live in ONE stacked buffer per
-        # parity, so a whole batch can arrive with a single copy (submit_stacked)
+        # slot, so a whole batch can arrive with a single copy (submit_stacked)
         self._stacked = None
         if all(t.shape == map_designs.shape and t.dtype == map_designs.dtype for t in examples):
-            self._stacked = [torch.empty((3,) + tuple(map_designs.shape), dtype=map_designs.dtype, device=dev) for _ in range(2)]
+            self._stacked = [torch.empty((3,) + tuple(map_designs.shape), dtype=map_designs.dtype, device=dev)
+                             for _ in range(n_in)]
             self._in = [tuple(st[i] for i in range(3)) for st in self._stacked]
         else:
-            self._in = [tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in examples) for _ in range(2)]
+            self._in = [tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in examples) for _ in range(n_in)]
         for buf in self._in:
             for dst, src in zip(buf, examples):
                 dst.copy_(src)
@@ -173,7 +196,7 @@ class PipelinedPlanner:
         self._taps = [torch.empty_like(taps) for _ in range(2)]
         self._host_in = self._host_out = None
         if host:
-            self._host_in = [tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in examples) for _ in range(2)]
+            self._host_in = [tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in examples) for _ in range(n_in)]
             for buf in self._host_in:
                 for dst, src in zip(buf, examples):
                     dst.copy_(src)
@@ -181,6 +204,7 @@ class PipelinedPlanner:
             self._host_out = [(torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory(),
                                torch.empty((B, 1, H, W), dtype=torch.int64).pin_memory()) for _ in range(2)]
         self._side = torch.cuda.Stream(device=dev)
+        self._copy = torch.cuda.Stream(device=dev) if host else None
         self._graphs = {}
         self._outs = {}
         self._k = 0            # batches submitted so far
@@ -192,104 +216,139 @@ class PipelinedPlanner:
         self._per_graph = {}
 
     # -- building blocks ---------------------------------------------------------------------------------
-    def _encode(self, ins, out=None):
+    def _encode(self, ins, out=None, on_last_conv=None):
         p = self.planner
-        return p._head_taps(*ins, out=out)
+        return p._head_taps(*ins, out=out, on_last_conv=on_last_conv)
 
-    def _search(self, par):
+    def _search(self, in_idx: int, taps_idx: int):
         p = self.planner
-        ins = self._in[par]
+        ins = self._in[in_idx]
         passable = torch.ones_like(ins[1]) if p.learn_obstacles else ins[0]
-        return p.astar.search_from_taps(self._taps[par], self._bias, self._scale, ins[1], ins[2], passable)
+        return p.astar.search_from_taps(self._taps[taps_idx], self._bias, self._scale, ins[1], ins[2], passable)
 
-    def _graph(self, kind: str, par: int):
-        """kind: 'enc' (first batch), 'full' (search of batch k-1 on parity 1-par  ||  encoder of batch k on par),
-        'search' (last batch, parity par)."""
-        key = (kind, par)
+    def _step_graph(self, k: int, copy: bool, enc: bool, search: bool):
+        """One step as a graph.  Host pipeline: `copy` = H2D of batch k, `enc` = encoder of batch k-1, `search` = search
+        (+ D2H) of batch k-2.  Device pipeline (no copy stage): `enc` = encoder of batch k, `search` = search of batch
+        k-1.  Buffer slots depend on k only through k mod 6 (inputs cycle mod 3 or 2, encoder outputs mod 2)."""
+        lag = 1 if self.host else 0
+        n_in = len(self._in)
+        key = (k % (6 if self.host else 2), copy, enc, search)
         if key in self._graphs:
-            return self._graphs[key]
+            return key
+        e, s_ = k - lag, k - lag - 1           # batch numbers of the encoder / search stage
         torch.cuda.synchronize(self.device)
         before = self._native.launch_count()
         g = torch.cuda.CUDAGraph()
-        out = None
         with torch.cuda.graph(g), torch.no_grad():
             main = torch.cuda.current_stream(self.device)
-            if kind in ("full", "search"):
-                spar = (1 - par) if kind == "full" else par
+            forked = []
+
+            def fork_search():
+                if forked:
+                    return
                 self._side.wait_stream(main)                       # fork
                 with torch.cuda.stream(self._side):
-                    out = self._search(spar)
+                    res = self._search(s_ % n_in, s_ % 2)
                     if self.host:
-                        self._host_out[spar][0].copy_(out.histories, non_blocking=True)
-                        self._host_out[spar][1].copy_(out.paths, non_blocking=True)
-            if kind in ("full", "enc"):
-                if self.host:
-                    for d, h in zip(self._in[par], self._host_in[par]):
+                        self._host_out[s_ % 2][0].copy_(res.histories, non_blocking=True)
+                        self._host_out[s_ % 2][1].copy_(res.paths, non_blocking=True)
+                forked.append(res)
+
+            if copy:
+                self._copy.wait_stream(main)                       # fork
+                with torch.cuda.stream(self._copy):
+                    for d, h in zip(self._in[k % n_in], self._host_in[k % n_in]):
                         d.copy_(h, non_blocking=True)
-                self._encode(self._in[par], out=self._taps[par])
-            if kind in ("full", "search"):
+            if search and (self.fork == "early" or not enc):
+                fork_search()
+            if enc:
+                self._encode(self._in[e % n_in], out=self._taps[e % 2], on_last_conv=fork_search if search else None)
+            if search:
+                fork_search()                                      # encoders that never reached the hook
                 main.wait_stream(self._side)                       # join
+            if copy:
+                main.wait_stream(self._copy)                       # join
         self._graphs[key] = g
-        self._outs[key] = out
+        self._outs[key] = forked[0] if forked else None
         self._per_graph[key] = self._native.launch_count() - before
-        return g
+        return key
+
+    def _run(self, key):
+        self._graphs[key].replay()
+        self.replays += 1
+        self.native_launches += self._per_graph[key]
+        return self._outs[key]
 
     # -- public API --------------------------------------------------------------------------------------
     @property
+    def depth(self) -> int:
+        """Stages between submit(batch k) and its results: 2 (device inputs) or 3 (host=True)."""
+        return 3 if self.host else 2
+
+    @property
     def host_inputs(self):
-        """[(map_designs, start_maps, goal_maps)] x 2 pinned staging buffers; batch k is read from index k % 2."""
+        """[(map_designs, start_maps, goal_maps)] x 3 pinned staging buffers; batch k is read from index k % 3."""
         return self._host_in
 
     @property
     def host_outputs(self):
-        """[(histories, paths)] x 2 pinned result buffers; batch k lands in index k % 2."""
+        """[(histories, paths)] x 2 pinned result buffers; batch k lands in index k % 2 during submit() number k+2
+        (or drain())."""
         return self._host_out
 
     def submit(self, map_designs: Optional[torch.Tensor] = None, start_maps: Optional[torch.Tensor] = None,
                goal_maps: Optional[torch.Tensor] = None) -> Optional[AstarOutput]:
-        """Enqueue batch k (device tensors; omit them with host=True, the batch is then read from
-        host_inputs[k % 2]).  Returns the graph-owned outputs of batch k-1 (overwritten two submits later)."""
-        par = self._k & 1
-        if not self.host:
-            for dst, src in zip(self._in[par], (map_designs, start_maps, goal_maps)):
+        """Enqueue batch k.  Device pipeline: pass the three device tensors; returns the graph-owned outputs of batch
+        k-1 (overwritten two submits later), None for the first batch.  host=True: pass nothing, the batch is read
+        from host_inputs[k % 3]; returns the device outputs of batch k-2 (None for the first two) whose copies are
+        landing in host_outputs[k % 2]."""
+        k = self._k
+        if self.host:
+            key = self._step_graph(k, True, k >= 1, k >= 2)
+        else:
+            for dst, src in zip(self._in[k & 1], (map_designs, start_maps, goal_maps)):
                 dst.copy_(src, non_blocking=True)
-        kind = "enc" if self._k == 0 else "full"
-        g = self._graph(kind, par)
-        g.replay()
-        self.replays += 1
-        self.native_launches += self._per_graph[(kind, par)]
+            key = self._step_graph(k, False, True, k >= 1)
         self._k += 1
-        return self._outs[(kind, par)]
+        return self._run(key)
 
     def submit_stacked(self, batch: torch.Tensor) -> Optional[AstarOutput]:
         """submit() for a batch delivered as one [3, B, 1, H, W] tensor (map_designs, start_maps, goal_maps stacked):
         a single device copy instead of three."""
         if self._stacked is None or self.host:
             raise ValueError("submit_stacked needs equally shaped inputs and a device-input pipeline")
-        par = self._k & 1
-        self._stacked[par].copy_(batch, non_blocking=True)
-        kind = "enc" if self._k == 0 else "full"
-        self._graph(kind, par).replay()
-        self.replays += 1
-        self.native_launches += self._per_graph[(kind, par)]
+        k = self._k
+        self._stacked[k & 1].copy_(batch, non_blocking=True)
+        key = self._step_graph(k, False, True, k >= 1)
         self._k += 1
-        return self._outs[(kind, par)]
+        return self._run(key)
 
     def drain(self) -> Optional[AstarOutput]:
-        """Finish the last submitted batch; the pipeline is empty afterwards."""
-        if self._k == 0:
+        """Finish every submitted batch; returns the outputs of the last one.  The pipeline is empty afterwards."""
+        k = self._k
+        if k == 0:
             return None
-        par = (self._k - 1) & 1
-        g = self._graph("search", par)
-        g.replay()
-        self.replays += 1
-        self.native_launches += self._per_graph[("search", par)]
+        out = None
+        if self.host:
+            out = self._run(self._step_graph(k, False, True, k >= 2))         # encoder(k-1) || search(k-2)
+            out = self._run(self._step_graph(k + 1, False, False, True))      # search(k-1)
+        else:
+            out = self._run(self._step_graph(k, False, False, True))          # search(k-1)
         self._k = 0
-        return self._outs[("search", par)]
+        return out
 
     def prepare(self) -> None:
         """Capture every graph variant now (otherwise captured lazily on first use, which synchronises)."""
-        self._graph("enc", 0)
-        for par in (0, 1):
-            self._graph("full", par)
-            self._graph("search", par)
+        if self.host:
+            self._step_graph(0, True, False, False)
+            self._step_graph(1, True, True, False)
+            self._step_graph(1, False, True, False)                          # drain after a single batch
+            for k in range(2, 8):
+                self._step_graph(k, True, True, True)
+                self._step_graph(k, False, True, True)
+                self._step_graph(k, False, False, True)
+        else:
+            self._step_graph(0, False, True, False)
+            for k in (1, 2):
+                self._step_graph(k, False, True, True)
+                self._step_graph(k, False, False, True)

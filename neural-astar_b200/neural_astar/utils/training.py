@@ -198,7 +198,7 @@ class PlannerModule(_ModuleBase):
         if pl is not None:
             self.log(name, value)
         else:
-            self.__dict__.setdefault("logged", {})[name] = float(value)
+            self.__dict__.setdefault("logged", {})[name] = float(value.detach() if torch.is_tensor(value) else value)
 
     def fit(self, train_loader, val_loader=None, num_epochs: int = 1, device="cuda"):
         """Plain-PyTorch stand-in for pl.Trainer.fit, driving the same step functions."""

@@ -454,7 +454,8 @@ def test_end_to_end_masks_on_all_1000_maps():
 
 
 # ------------------------------------------------------------------------------------------------ graphs / pipeline
-def test_pipelined_and_host_graphs_match_eager():
+@pytest.mark.parametrize("fork", ["late", "early"])
+def test_pipelined_and_host_graphs_match_eager(fork):
     from neural_astar.utils.inference import GraphedPlanner, PipelinedPlanner
 
     g = Golden("mazes032_vanilla_test")
@@ -468,7 +469,7 @@ def test_pipelined_and_host_graphs_match_eager():
     with torch.no_grad():
         want = [na(*b) for b in batches]
     # device-resident pipeline
-    pipe = PipelinedPlanner(na, maps, start, goal)
+    pipe = PipelinedPlanner(na, maps, start, goal, fork=fork)
     got = []
     for b in batches:
         prev = pipe.submit(*b)
@@ -487,21 +488,41 @@ def test_pipelined_and_host_graphs_match_eager():
             assert torch.equal(prev.histories, want[k - 1].histories)
     last = pipe.drain()
     assert torch.equal(last.histories, want[2].histories) and torch.equal(last.paths, want[2].paths)
-    # host pipeline: pinned in, pinned out, copies inside the graphs
-    pipe = PipelinedPlanner(na, maps, start, goal, host=True)
+    # host pipeline (three stages: H2D(k) || encoder(k-1) || search(k-2) + D2H): pinned in, pinned out
+    pipe = PipelinedPlanner(na, maps, start, goal, host=True, fork=fork)
+    assert pipe.depth == 3 and len(pipe.host_inputs) == 3 and len(pipe.host_outputs) == 2
     results = []
     for k, b in enumerate(batches):
-        for dst, src in zip(pipe.host_inputs[k % 2], b):
+        torch.cuda.synchronize()                    # the staging buffer's previous batch has been consumed
+        for dst, src in zip(pipe.host_inputs[k % 3], b):
             dst.copy_(src.cpu())
-        pipe.submit()
-        if k >= 1:
+        out = pipe.submit()
+        assert (out is None) == (k < 2)
+        if k >= 2:
             torch.cuda.synchronize()
-            results.append(tuple(t.clone() for t in pipe.host_outputs[(k - 1) % 2]))
-    pipe.drain()
+            assert torch.equal(out.histories, want[k - 2].histories)
+            results.append(tuple(t.clone() for t in pipe.host_outputs[(k - 2) % 2]))
+    last = pipe.drain()
     torch.cuda.synchronize()
-    results.append(tuple(t.clone() for t in pipe.host_outputs[(len(batches) - 1) % 2]))
+    n = len(batches)
+    assert torch.equal(last.histories, want[n - 1].histories)
+    results.append(tuple(t.clone() for t in pipe.host_outputs[(n - 2) % 2]))
+    results.append(tuple(t.clone() for t in pipe.host_outputs[(n - 1) % 2]))
+    assert len(results) == n
     for (h, p), w in zip(results, want):
         assert torch.equal(h, w.histories.cpu()) and torch.equal(p, w.paths.cpu())
+    # short runs: drain after one and after two batches
+    for n_short in (1, 2):
+        for k in range(n_short):
+            for dst, src in zip(pipe.host_inputs[k % 3], batches[k]):
+                dst.copy_(src.cpu())
+            assert pipe.submit() is None
+        last = pipe.drain()
+        torch.cuda.synchronize()
+        assert torch.equal(last.histories, want[n_short - 1].histories)
+        for k in range(n_short):
+            assert torch.equal(pipe.host_outputs[k % 2][1], want[k].paths.cpu())
+    assert pipe.drain() is None
     # single-graph end-to-end replay
     fast = GraphedPlanner(na, maps, start, goal)
     for dst, src in zip(fast.host_inputs, batches[2]):
