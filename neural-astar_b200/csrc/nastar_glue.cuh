@@ -134,10 +134,11 @@ __global__ void __launch_bounds__(32 * kConv1Warps) conv1_marks_kernel(const flo
 // 1.2 TB/s on it (86 us).  Here: one thread per pixel keeps the 9 sums in registers; the C*9 weights arrive as a
 // by-value kernel parameter, i.e. in the constant bank, so every FFMA takes its weight operand straight from a uniform
 // register — no weight loads at all.  The activation is staged through shared memory: a warp copies its 32 pixels'
-// channel slice (32 x kSlice floats, contiguous 4*kSlice-byte runs) with fully coalesced 16-byte cp.async, then every
-// lane reads its own pixel's row back with conflict-free LDS.128 (row stride kSlice+4 floats).  Measured at b=100,
-// 32x32, C=256 (105 MB read, profiles/README.md): 26.5 us under ncu = 4.0 TB/s; torch.sum over the same tensor takes
-// 25 us.  Two alternatives were measured and dropped: each lane streaming its own 1 KB row straight from global memory
+// channel slice (32 x 32 floats, one 128-byte line per pixel) with fully coalesced 16-byte cp.async into one of its two
+// buffers while it multiplies the slice in the other, and every lane reads its own pixel's row back with conflict-free
+// LDS.128 (row stride 36 floats).  Measured at b=100, 32x32, C=256 (105 MB read, profiles/README.md): 24.8 us under
+// ncu, 26.8 us with CUDA events = 3.9 TB/s; torch.sum over the same tensor takes 25.0 us.  Measured and dropped: the same
+// staging single-buffered with 64-channel slices (26.5 us under ncu), each lane streaming its own 1 KB row straight from global memory
 // (every LDG.128 touches 32 different lines: 31 us), and a CTA-cooperative version with whole 32 KB tiles in a
 // cp.async ring and one channel slice per warp (weights per warp either as 8 separately unrolled constant-bank blocks
 // — instruction-cache thrash, 124 us — or as broadcast LDS.128 from shared memory — MIO-throttled, 37 us).
@@ -148,50 +149,71 @@ struct HeadWeights {
 };
 
 constexpr int kHeadWarps = 4;
+constexpr int kHeadSlice = 32;                       // channels staged per pass (128 contiguous bytes per pixel)
+
+template <int C>
+__device__ __forceinline__ void head_issue_slice(const float* __restrict__ x, int64_t P, int64_t p0, int s0, uint32_t dst_s,
+                                                 int lane) {
+    constexpr int kRow = kHeadSlice + 4, kChunks = kHeadSlice / 4;
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {              // 32 lanes x kChunks copies of 16 B = the 32 x kHeadSlice tile
+        const int idx = i * 32 + lane;
+        const int px = idx / kChunks, ch = idx % kChunks;
+        int64_t p = p0 + px;
+        p = p < P ? p : P - 1;                       // ragged last group: re-read the last pixel, never stored
+        const float* src = x + p * C + s0 + ch * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s + uint32_t(px * kRow + ch * 4) * 4u), "l"(src)
+                     : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 template <int C>
 __global__ void __launch_bounds__(32 * kHeadWarps) head_taps_kernel(const float* __restrict__ x, int64_t P,
                                                                     const __grid_constant__ HeadWeights<C> hw,
                                                                     float* __restrict__ out) {
-    constexpr int kSlice = C < 64 ? C : 64;          // channels staged per pass
-    constexpr int kRow = kSlice + 4;                 // padded row (floats): 16 B aligned, quarter-warps hit 32 distinct banks
-    constexpr int kChunks = kSlice / 4;              // float4 per pixel and slice
-    __shared__ __align__(16) float sX[kHeadWarps][32 * kRow];
+    constexpr int kRow = kHeadSlice + 4;             // padded row (floats): 16 B aligned, quarter-warps hit 32 distinct banks
+    constexpr int kChunks = kHeadSlice / 4;          // float4 per pixel and slice
+    constexpr int kSlices = C / kHeadSlice;
+    __shared__ __align__(16) float sX[kHeadWarps][2][32 * kRow];   // per warp: two slices in flight / in use
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* st = sX[warp];
-    const uint32_t st_s = uint32_t(__cvta_generic_to_shared(st));
+    const uint32_t st_s = uint32_t(__cvta_generic_to_shared(&sX[warp][0][0]));
     const int64_t groups = (P + 31) / 32;
-    for (int64_t grp = int64_t(blockIdx.x) * kHeadWarps + warp; grp < groups; grp += int64_t(gridDim.x) * kHeadWarps) {
+    const int64_t gstride = int64_t(gridDim.x) * kHeadWarps;
+    int64_t grp = int64_t(blockIdx.x) * kHeadWarps + warp;
+    if (grp >= groups) return;
+    int buf = 0;
+    head_issue_slice<C>(x, P, grp * 32, 0, st_s, lane);
+    for (; grp < groups; grp += gstride) {
         const int64_t p0 = grp * 32;
         float acc[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) acc[k] = 0.f;
 #pragma unroll
-        for (int s0 = 0; s0 < C; s0 += kSlice) {
-#pragma unroll
-            for (int i = 0; i < kChunks; ++i) {      // 32 lanes x kChunks copies of 16 B = the 32 x kSlice tile
-                const int idx = i * 32 + lane;
-                const int px = idx / kChunks, ch = idx % kChunks;
-                int64_t p = p0 + px;
-                p = p < P ? p : P - 1;               // ragged last group: re-read the last pixel, never stored
-                const float* src = x + p * C + s0 + ch * 4;
-                const uint32_t dst = st_s + uint32_t(px * kRow + ch * 4) * 4u;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.wait_all;" ::: "memory");
+        for (int sl = 0; sl < kSlices; ++sl) {
+            // prefetch the next slice (of this group, or the first slice of the warp's next group) into the other buffer
+            const bool last = (sl == kSlices - 1);
+            const int64_t gn = last ? grp + gstride : grp;
+            if (gn < groups)
+                head_issue_slice<C>(x, P, gn * 32, last ? 0 : (sl + 1) * kHeadSlice, st_s + uint32_t((buf ^ 1) * 32 * kRow) * 4u, lane);
+            else
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
             __syncwarp();
+            const float* st = &sX[warp][buf][0];
 #pragma unroll
             for (int c4 = 0; c4 < kChunks; ++c4) {
                 const float4 v = *reinterpret_cast<const float4*>(st + lane * kRow + c4 * 4);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
-                    acc[k] = fmaf(v.x, hw.w[(s0 + 4 * c4 + 0) * 9 + k], acc[k]);
-                    acc[k] = fmaf(v.y, hw.w[(s0 + 4 * c4 + 1) * 9 + k], acc[k]);
-                    acc[k] = fmaf(v.z, hw.w[(s0 + 4 * c4 + 2) * 9 + k], acc[k]);
-                    acc[k] = fmaf(v.w, hw.w[(s0 + 4 * c4 + 3) * 9 + k], acc[k]);
+                    acc[k] = fmaf(v.x, hw.w[(sl * kHeadSlice + 4 * c4 + 0) * 9 + k], acc[k]);
+                    acc[k] = fmaf(v.y, hw.w[(sl * kHeadSlice + 4 * c4 + 1) * 9 + k], acc[k]);
+                    acc[k] = fmaf(v.z, hw.w[(sl * kHeadSlice + 4 * c4 + 2) * 9 + k], acc[k]);
+                    acc[k] = fmaf(v.w, hw.w[(sl * kHeadSlice + 4 * c4 + 3) * 9 + k], acc[k]);
                 }
             }
-            __syncwarp();                            // all lanes done reading before the next slice overwrites the tile
+            __syncwarp();                            // all lanes done reading before this buffer is refilled
+            buf ^= 1;
         }
         if (p0 + lane < P) {
             float* o = out + (p0 + lane) * 9;
@@ -199,6 +221,7 @@ __global__ void __launch_bounds__(32 * kHeadWarps) head_taps_kernel(const float*
             for (int k = 0; k < 9; ++k) o[k] = acc[k];
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 }  // namespace nastar
