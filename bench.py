@@ -604,7 +604,6 @@ def bench_ours(args):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version / debug lines off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         dist = None
