@@ -531,19 +531,17 @@ def config_c5(dev, peak, rank, timer, dist, world):
     # drains, so the next batch's CTAs move onto the SMs the current batch has already vacated while its last, longest
     # maps are still being searched on a few SMs.  Every launch does its full work and completes inside the timed region.
     n_streams, reps_t = 4, 16
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    from neural_astar.planner import VanillaAstar
+    from neural_astar.utils.inference import OverlappedPlanner
+
+    over = OverlappedPlanner(VanillaAstar().to(dev).eval(), n_streams=n_streams, device=dev)
 
     def overlapped(n):
-        main = torch.cuda.current_stream(dev)
         last = None
-        for st in streams:
-            st.wait_stream(main)
-        for i in range(n):
-            with torch.cuda.stream(streams[i % n_streams]):
-                last = fn()
-        for st in streams:
-            main.wait_stream(st)
-        return last
+        for _ in range(n):
+            last = over.submit(o, s, g)
+        over.wait_all()
+        return last.result()
 
     overlapped(2 * n_streams)
     trials_t = []
@@ -551,7 +549,7 @@ def config_c5(dev, peak, rank, timer, dist, world):
         t_ms, out_t = timer.loop(lambda: overlapped(reps_t))
         trials_t.append(t_ms / reps_t)
     ms = sorted(trials_t)[1]
-    assert torch.equal(out_t[0], out[0]) and torch.equal(out_t[1], out[1])     # same results as the serial launch
+    assert torch.equal(out_t.histories, out[0]) and torch.equal(out_t.paths, out[1])   # same results as the serial launch
     ns = out[3].float()
     stats = torch.tensor([ms, float(ns.sum()), float(ns.max()), float((out[2] >= 0).sum()), ms_serial], device=dev,
                          dtype=torch.float64)
@@ -573,7 +571,7 @@ def config_c5(dev, peak, rank, timer, dist, world):
     return {"workload": f"VanillaAstar, synthetic 256x256 Moore grids (p_obst 0.2, Chebyshev(start,goal) >= 128), "
                         f"{per_gpu} distinct maps per GPU x {world} GPU(s), seed 1234+rank",
             "maps_per_s": maps_total / (ms * 1e-3), "maps_per_s_per_gpu": per_gpu / (ms * 1e-3), "ms_per_batch": ms,
-            "throughput_mode": f"{reps_t} launches round-robin on {n_streams} streams, max over ranks (tails of one batch "
+            "throughput_mode": f"utils.inference.OverlappedPlanner(VanillaAstar): {reps_t} batches round-robin on {n_streams} streams, max over ranks (tails of one batch "
                                "overlap the next batches); `serial` = one launch at a time",
             "ms_per_batch_trials": trials_t,
             "serial": {"ms_per_launch": ms_serial, "ms_per_launch_trials": trials, "maps_per_s": maps_total / (ms_serial * 1e-3),

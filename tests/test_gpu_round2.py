@@ -531,3 +531,38 @@ def test_pipelined_and_host_graphs_match_eager(fork):
     torch.cuda.synchronize()
     assert torch.equal(fast.host_outputs[0], want[2].histories.cpu())
     assert torch.equal(fast.host_outputs[1], want[2].paths.cpu())
+
+
+def test_overlapped_planner_matches_direct_calls():
+    """OverlappedPlanner: batches round-robin on several streams give exactly the direct call's outputs (engine 5 on
+    136x144 binary maps, the warp engine on 32x32 learned costs)."""
+    from neural_astar.planner import VanillaAstar
+    from neural_astar.utils.inference import OverlappedPlanner
+
+    rng = np.random.RandomState(7)
+    va = VanillaAstar().cuda().eval()
+    batches = []
+    for k in range(6):
+        H, W = (136, 144) if k % 2 == 0 else (40, 33)
+        o = (rng.rand(5, 1, H, W) > 0.2).astype(np.float32)
+        s = np.zeros_like(o); g = np.zeros_like(o)
+        o[:, 0, 0, 0] = o[:, 0, -1, -1] = 1; s[:, 0, 0, 0] = 1; g[:, 0, -1, -1] = 1
+        batches.append(tuple(_cu(x) for x in (o, s, g)))
+    with torch.no_grad():
+        want = [va(*b) for b in batches]
+    over = OverlappedPlanner(va, n_streams=3, device="cuda")
+    handles = [over.submit(*b) for b in batches]
+    for h, w in zip(handles, want):
+        out = h.result()
+        assert torch.equal(out.histories, w.histories) and torch.equal(out.paths, w.paths)
+    h = over.submit(*batches[0])
+    over.wait_all()
+    torch.cuda.synchronize()
+    assert h.done() and torch.equal(h.result().paths, want[0].paths)
+    na = _ckpt_planner()
+    g_ = Golden("mazes032_vanilla_test")
+    b = tuple(_cu(x) for x in (g_.obst, g_.start, g_.goal))
+    with torch.no_grad():
+        w = na(*b)
+    outs = [OverlappedPlanner(na, n_streams=2).submit(*b).result() for _ in range(2)]
+    assert all(torch.equal(o.histories, w.histories) for o in outs)
