@@ -8,9 +8,10 @@ uniform costs, which is what the reference's own test pins (tests/astar_test.py:
 planner/pq_astar.py for the cost-convention difference with learned costs.
 
 Inference hand-off: in eval / no-grad mode on CUDA, `NeuralAstar.forward` runs
-`pack_inputs` (one kernel: start+goal add, nearest upsample, concat, NHWC) -> the encoder's cuDNN convs ->
-the head's skinny GEMM -> the search kernel, whose prologue finishes the encoder (9-tap gather + bias,
-sigmoid, * const: encoder.py:32-34) — no ATen glue launches in between.
+the input assembly (start+goal add, nearest upsample, concat, NHWC) as one kernel — folded into the first
+convolution for the "m+" CNN (`conv1_marks`), a separate `pack_inputs` otherwise -> the encoder's cuDNN convs ->
+the head's per-pixel products (`head_taps`) -> the search kernel, whose prologue finishes the encoder (9-tap
+gather + bias, sigmoid, * const: encoder.py:32-34) — no ATen glue launches in between.
 """
 from __future__ import annotations
 

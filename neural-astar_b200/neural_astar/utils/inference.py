@@ -1,8 +1,8 @@
 """CUDA-graph replay and encoder/search pipelining of a planner's inference forward for fixed batch shapes.
 
-An eager `planner(map_designs, start_maps, goal_maps)` issues about ten launches from Python (pack kernel, encoder
-convs, head GEMM, search kernel); at 32x32 / batch 100 the GPU work is ~0.3 ms, so the step is close to
-CPU-launch bound and slows down further when several ranks share a host.
+An eager `planner(map_designs, start_maps, goal_maps)` issues half a dozen launches from Python (first layer /
+pack kernel, encoder convs, head kernel, search kernel); at 32x32 / batch 100 the GPU work is ~0.23 ms, so the step is
+close to CPU-launch bound and slows down further when several ranks share a host.
 
     fast = GraphedPlanner(planner, map_designs, start_maps, goal_maps)   # example batch fixes shapes/dtypes
     out = fast(map_designs, start_maps, goal_maps)                        # AstarOutput, caller-owned tensors
