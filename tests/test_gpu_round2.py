@@ -566,3 +566,47 @@ def test_overlapped_planner_matches_direct_calls():
         w = na(*b)
     outs = [OverlappedPlanner(na, n_streams=2).submit(*b).result() for _ in range(2)]
     assert all(torch.equal(o.histories, w.histories) for o in outs)
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_pipelined_planner_downsizing_encoder(host):
+    """PipelinedPlanner on the WarCraft-shaped planner (rgb+ input packed by pack_inputs, CNNDownSize with pooling,
+    learn_obstacles): same outputs as the eager call, late fork (hook before the last conv) and host staging."""
+    from neural_astar.planner import NeuralAstar
+    from neural_astar.utils.inference import PipelinedPlanner
+
+    torch.manual_seed(5)
+    na = NeuralAstar(encoder_input="rgb+", encoder_arch="CNNDownSize", encoder_depth=3, learn_obstacles=True,
+                     const=10.0).cuda().eval()
+    B = 16
+    batches = []
+    for k in range(4):
+        maps = torch.rand(B, 3, 96, 96, device="cuda")
+        s = torch.zeros(B, 1, 12, 12, device="cuda"); s[:, :, k, 0] = 1
+        g = torch.zeros_like(s); g[:, :, 11, 11 - k] = 1
+        batches.append((maps, s, g))
+    with torch.no_grad():
+        want = [na(*b) for b in batches]
+    pipe = PipelinedPlanner(na, *batches[0], host=host, fork="late")
+    got = []
+    for k, b in enumerate(batches):
+        if host:
+            torch.cuda.synchronize()
+            for dst, src in zip(pipe.host_inputs[k % 3], b):
+                dst.copy_(src.cpu())
+            out = pipe.submit()
+        else:
+            out = pipe.submit(*b)
+        if out is not None:
+            got.append((out.histories.clone(), out.paths.clone()))
+    if host:                        # drain runs two steps: batch n-2, then batch n-1 (returned)
+        last = pipe.drain()
+        torch.cuda.synchronize()
+        assert torch.equal(pipe.host_outputs[(len(batches) - 2) % 2][0], want[-2].histories.cpu())
+        got.append((want[-2].histories, want[-2].paths))
+    else:
+        last = pipe.drain()
+    got.append((last.histories.clone(), last.paths.clone()))
+    assert len(got) == len(batches)
+    for (h, p), w in zip(got, want):
+        assert torch.equal(h, w.histories) and torch.equal(p, w.paths)
