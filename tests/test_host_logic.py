@@ -91,6 +91,37 @@ def test_invalid_arguments_are_rejected_without_a_gpu(built_lib):
     assert L.nastar_b200_backward(None, None) == 1
 
 
+def test_glue_entry_points_reject_bad_arguments_without_a_gpu(built_lib):
+    """The encoder-side entry points validate before launching: null pointers / sizes at the C ABI, CPU tensors and wrong
+    weight layouts in the binding (no compute call is made on this box)."""
+    import numpy as np
+
+    L = built_lib.lib()
+    assert L.nastar_b200_conv1_marks(None, None, 0, None, 0, 1, 8, 8, None, None, None, None) == 1
+    assert L.nastar_b200_head_taps(None, 64, 256, None, None, None) == 1
+    assert L.nastar_b200_pack_inputs is not None and L.nastar_b200_cost_from_taps is not None
+    maps = torch.ones(2, 1, 8, 8)
+    marks = torch.zeros(2, 1, 8, 8)
+    w = np.zeros((9, 2, 32), np.float32)
+    b = np.zeros((32,), np.float32)
+    with pytest.raises(ValueError):
+        built_lib.conv1_marks(maps, marks, marks, w, b)                      # CPU tensors
+    with pytest.raises((ValueError, AttributeError)):
+        built_lib.conv1_marks(maps, marks, marks, w.reshape(18, 32), b)      # wrong weight layout
+
+
+def test_stream_helpers_validate_arguments():
+    from neural_astar.planner import VanillaAstar
+    from neural_astar.utils.inference import OverlappedPlanner, PipelinedPlanner
+
+    with pytest.raises(ValueError):
+        OverlappedPlanner(VanillaAstar(), n_streams=0)
+    with pytest.raises(ValueError):
+        OverlappedPlanner(VanillaAstar(), device="cpu")
+    with pytest.raises(TypeError):
+        PipelinedPlanner(VanillaAstar(), torch.ones(1, 1, 8, 8), torch.ones(1, 1, 8, 8), torch.ones(1, 1, 8, 8))
+
+
 def test_no_cpu_fallback(built_lib):
     """CPU tensors are refused loudly; the product never routes through the oracle or eager PyTorch."""
     from neural_astar.planner import VanillaAstar
