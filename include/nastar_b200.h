@@ -61,7 +61,8 @@ enum {
                                 fp32 [B][H*W][9] (tap k = ky*3+kx innermost): the prologue gathers
                                 x[y][x] = cost_bias + sum_k taps[y+ky-1][x+kx-1][k] (zero padding), then
                                 cost = sigmoid(x) * cost_scale.  `cost_stride` is in elements of this layout
-                                (9*H*W for a dense batch).  Engine-1 shapes only */
+                                (9*H*W for a dense batch).  LOGIT / TAPS: engines 1 and 4 (H,W <= 64),
+                                NASTAR_EUNSUPPORTED for larger shapes */
 
 typedef struct nastar_fwd_params {
     /* inputs — differentiable_astar.py:150-157 (cost_maps, start_maps, goal_maps, obstacles_maps) */

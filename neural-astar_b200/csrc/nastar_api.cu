@@ -179,7 +179,7 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const int engine = nastar_b200_engine_for(p->H, p->W);
     if (engine == 0) return NASTAR_EUNSUPPORTED;
-    if (p->cost_kind != NASTAR_COST_PLANE && engine != 1) return NASTAR_EUNSUPPORTED;   // fused hand-off: H,W <= 32
+    if (p->cost_kind != NASTAR_COST_PLANE && engine != 1 && engine != 4) return NASTAR_EUNSUPPORTED;   // fused hand-off: H,W <= 64
     const bool pair = (p->flags & NASTAR_FWD_PAIR) != 0;
     if (pair && engine != 1) {
         // two halves back to back: the learned-cost search, then the same problems with cost = obstacles
@@ -190,6 +190,7 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
         if (st != NASTAR_OK) return st;
         h.cost = p->obst;
         h.cost_stride = p->obst_stride;
+        h.cost_kind = NASTAR_COST_PLANE;
         h.histories = p->histories + int64_t(p->B) * N;
         h.paths = p->paths + int64_t(p->B) * N;
         if (p->t_solve) h.t_solve = p->t_solve + p->B;
@@ -234,7 +235,10 @@ int nastar_b200_forward(const nastar_fwd_params* p, void* stream_v) {
             return cudaSuccess;
         };
         cudaError_t e;
-        if (p->trace) e = noexit ? launch(nastar::astar_warp64_kernel<true, true>) : launch(nastar::astar_warp64_kernel<true, false>);
+        if (p->cost_kind != NASTAR_COST_PLANE) {
+            if (p->trace) e = noexit ? launch(nastar::astar_warp64_kernel<true, true, false, true>) : launch(nastar::astar_warp64_kernel<true, false, false, true>);
+            else e = noexit ? launch(nastar::astar_warp64_kernel<false, true, false, true>) : launch(nastar::astar_warp64_kernel<false, false, false, true>);
+        } else if (p->trace) e = noexit ? launch(nastar::astar_warp64_kernel<true, true>) : launch(nastar::astar_warp64_kernel<true, false>);
         else e = noexit ? launch(nastar::astar_warp64_kernel<false, true>) : launch(nastar::astar_warp64_kernel<false, false>);
         if (e != cudaSuccess) return cuda_fail(e);
         g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -62,7 +62,9 @@ struct W64Args {
     float* grad_cost;
 };
 
-template <bool kTrace, bool kNoExit, bool kBwd = false>
+// kFused (forward only): the prologue may have to finish the encoder (NASTAR_COST_LOGIT / NASTAR_COST_TAPS), as in the
+// 32-wide engine; kept out of the plain instantiations.
+template <bool kTrace, bool kNoExit, bool kBwd = false, bool kFused = false>
 __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
     constexpr bool kContinue = kBwd || kNoExit;
     const nastar_fwd_params& p = a.f;
@@ -79,12 +81,14 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
     const float* gStart = p.start + int64_t(b) * p.start_stride;
     const float* gGoal = p.goal + int64_t(b) * p.goal_stride;
     const float* gObst = p.obst + int64_t(b) * p.obst_stride;
-    const bool obst_is_cost = (gObst == gCost);
+    const int cost_kind = (kFused && !kBwd) ? p.cost_kind : NASTAR_COST_PLANE;
+    const bool cost_plane = (cost_kind == NASTAR_COST_PLANE);
+    const bool obst_is_cost = cost_plane && (gObst == gCost);
 
     // ---------------- prologue ----------------------------------------------------------------
     u64 pass[2] = {0ull, 0ull};
     int start_rc = -1, goal_rc = -1;
-    const bool tma = (W == 64) && aligned16(gCost) && aligned16(gStart) && aligned16(gGoal) && aligned16(gObst);
+    const bool tma = (W == 64) && (!cost_plane || aligned16(gCost)) && aligned16(gStart) && aligned16(gGoal) && aligned16(gObst);
     if (tma) {
         float* tStart = reinterpret_cast<float*>(S.key);
         float* tGoal = reinterpret_cast<float*>(sGH);
@@ -94,13 +98,22 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
             mbar_init(bar, 1);
             fence_mbar_init();
             const uint32_t bytes = uint32_t(N) * 4u;
-            mbar_expect_tx(bar, bytes * (obst_is_cost ? 3u : 4u));
-            tma_load_1d(S.cost, gCost, bytes, bar);
+            mbar_expect_tx(bar, bytes * ((obst_is_cost ? 3u : 4u) - (cost_plane ? 0u : 1u)));
+            if (cost_plane) tma_load_1d(S.cost, gCost, bytes, bar);
             tma_load_1d(tStart, gStart, bytes, bar);
             tma_load_1d(tGoal, gGoal, bytes, bar);
             if (!obst_is_cost) tma_load_1d(tObst, gObst, bytes, bar);
         }
         __syncwarp();
+        if (kFused && !cost_plane) {
+            // fused encoder hand-off: the cost plane is produced here from the encoder's raw output while the TMA copies
+            // of the other planes are in flight
+#pragma unroll 2
+            for (int y = 0; y < H; ++y) {
+                S.cost[(y << 6) + lane] = cost_value(cost_kind, gCost, y, lane, H, W, p.cost_bias, p.cost_scale);
+                S.cost[(y << 6) + lane + 32] = cost_value(cost_kind, gCost, y, lane + 32, H, W, p.cost_bias, p.cost_scale);
+            }
+        }
         mbar_wait(bar, 0);
         const float* sObst = obst_is_cost ? S.cost : tObst;
 #pragma unroll 2
@@ -127,7 +140,8 @@ __global__ void __launch_bounds__(32) astar_warp64_kernel(const W64Args a) {
                 for (int hf = 0; hf < 2; ++hf) {
                     const bool ok = (hf ? in1 : in0) && (y0 + u < H);
                     const int i = (y0 + u) * W + lane + 32 * hf;
-                    vc[u][hf] = ok ? __ldg(gCost + i) : 0.f;
+                    vc[u][hf] = ok ? (kFused ? cost_value(cost_kind, gCost, y0 + u, lane + 32 * hf, H, W, p.cost_bias, p.cost_scale)
+                                             : __ldg(gCost + i)) : 0.f;
                     vo[u][hf] = obst_is_cost ? vc[u][hf] : (ok ? __ldg(gObst + i) : 0.f);
                     vs[u][hf] = ok ? __ldg(gStart + i) : 0.f;
                     vg[u][hf] = ok ? __ldg(gGoal + i) : 0.f;

@@ -192,7 +192,7 @@ def forward(cost: torch.Tensor, start: torch.Tensor, goal: torch.Tensor, obst: t
     `want_counts` a sixth element (n_closed [B'], path_len [B']) is appended.  B' = 2B with `pair`
     (NASTAR_FWD_PAIR: second half = the same problems with cost = obstacles), else B.
     `cost_kind` = COST_LOGIT / COST_TAPS: `cost` holds the encoder's raw output [B,1,H,W] / the 9-tap partial
-    products [B,H,W,9] and the kernel prologue finishes encoder.py:32-34 itself (H, W <= 32 only).
+    products [B,H,W,9] and the kernel prologue finishes encoder.py:32-34 itself (H, W <= 64 only).
     """
     L = lib()
     if not cost.is_cuda:

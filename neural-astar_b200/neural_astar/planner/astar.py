@@ -138,7 +138,7 @@ class NeuralAstar(VanillaAstar):
         T = self.astar.num_steps(W)
         kw = {}
         cost = None
-        if H <= 32 and W <= 32 and self.encoder.fast_path_ok(map_designs):
+        if H <= 64 and W <= 64 and self.encoder.fast_path_ok(map_designs):
             head = self._head_taps(map_designs, start_maps, goal_maps)
             if head is not None:
                 cost, bias, scale = head
@@ -152,10 +152,10 @@ class NeuralAstar(VanillaAstar):
     def _fused_forward(self, map_designs, start_maps, goal_maps, passable, store_intermediate_results):
         """Inference fast path: the search kernel consumes the encoder's 9-tap partial products directly
         (NASTAR_COST_TAPS), so no cost plane, sigmoid, bias add or layout conversion is launched.  Returns None
-        when it does not apply (training / autograd, CPU tensors, planning grids above 32x32, encoders without a
+        when it does not apply (training / autograd, CPU tensors, planning grids above 64x64, encoders without a
         single-output-channel conv head, g_ratio < 0.5 batches, pq_astar)."""
         H, W = start_maps.shape[-2], start_maps.shape[-1]
-        if (not self.use_differentiable_astar or not self.encoder.fast_path_ok(map_designs) or H > 32 or W > 32
+        if (not self.use_differentiable_astar or not self.encoder.fast_path_ok(map_designs) or H > 64 or W > 64
                 or not start_maps.is_cuda or (float(self.g_ratio) < 0.5 and start_maps.shape[0] > 1)
                 or start_maps.dtype != torch.float32 or passable.dtype != torch.float32):
             return None

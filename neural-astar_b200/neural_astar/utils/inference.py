@@ -256,7 +256,7 @@ class PipelinedPlanner:
         with torch.no_grad():
             head = self._encode(self._in[0])
         if head is None:
-            raise ValueError("this planner/shape has no fused encoder hand-off (needs a conv head and a grid <= 32x32)")
+            raise ValueError("this planner/shape has no fused encoder hand-off (needs a conv head and a grid <= 64x64)")
         taps, self._bias, self._scale = head
         self._taps = [torch.empty_like(taps) for _ in range(2)]
         self._host_in = self._host_out = None

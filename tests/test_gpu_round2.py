@@ -199,7 +199,7 @@ def test_sigmoid_prologue_is_bit_exact_with_torch(native):
 
 def test_cost_kinds_equal_plane_search(native):
     rng = np.random.RandomState(3)
-    for (H, W) in ((32, 32), (12, 12), (20, 31)):
+    for (H, W) in ((32, 32), (12, 12), (20, 31), (64, 64), (40, 57), (33, 64)):     # engine 1 and engine 4 shapes
         B = 6
         obst, start, goal = _corner_problem(rng, B, H, W, p_obst=0.1)
         s, g, o = _cu(start), _cu(goal), _cu(obst)
@@ -225,9 +225,9 @@ def test_cost_kinds_equal_plane_search(native):
         b = native.forward(taps, s, g, o, 0.5, W * W, cost_kind=native.COST_TAPS, cost_scale=scale, cost_bias=bias)
         for x, y in zip(a[:4], b[:4]):
             assert torch.equal(x, y)
-    with pytest.raises(RuntimeError):      # fused kinds are for H, W <= 32
-        big = torch.zeros((1, 1, 64, 64), device="cuda")
-        native.forward(big, big, big, big, 0.5, 64 * 64, cost_kind=native.COST_LOGIT)
+    with pytest.raises(RuntimeError):      # fused kinds are for H, W <= 64
+        big = torch.zeros((1, 1, 80, 80), device="cuda")
+        native.forward(big, big, big, big, 0.5, 80 * 80, cost_kind=native.COST_LOGIT)
 
 
 @pytest.mark.parametrize("C,B,H", [(256, 7, 32), (128, 5, 12), (64, 3, 20), (32, 2, 9)])
@@ -324,7 +324,9 @@ def test_pack_inputs_matches_torch(native, C, Hm, H):
 
 
 @pytest.mark.parametrize("arch,inp,depth,const,shape,hw", [("CNN", "m+", 4, None, (16, 1, 32, 32), 32),
-                                                            ("CNNDownSize", "rgb+", 3, 10.0, (8, 3, 96, 96), 12)])
+                                                            ("CNNDownSize", "rgb+", 3, 10.0, (8, 3, 96, 96), 12),
+                                                            ("CNN", "m+", 4, None, (6, 1, 64, 64), 64),
+                                                            ("CNN", "m+", 3, 5.0, (5, 1, 48, 48), 48)])
 def test_fused_forward_equals_unfused_composition(native, arch, inp, depth, const, shape, hw):
     """NeuralAstar.forward in eval mode (pack kernel -> convs -> head GEMM -> search with the TAPS prologue) gives
     exactly the outputs of encode() followed by the plain search: the cost arithmetic is one shared device function."""
@@ -610,3 +612,27 @@ def test_pipelined_planner_downsizing_encoder(host):
     assert len(got) == len(batches)
     for (h, p), w in zip(got, want):
         assert torch.equal(h, w.histories) and torch.equal(p, w.paths)
+
+
+@pytest.mark.parametrize("hw", [32, 64])
+def test_forward_pair_with_fused_handoff(hw):
+    """NeuralAstar.forward_pair (validation pair with the TAPS prologue): learned half == NeuralAstar.forward, vanilla
+    half == VanillaAstar, on the 32-wide engine (one launch) and the 64-wide engine (two halves back to back, the
+    second one on the plain obstacle plane)."""
+    from neural_astar.planner import NeuralAstar, VanillaAstar
+
+    torch.manual_seed(hw)
+    na = NeuralAstar(encoder_input="m+", encoder_arch="CNN", encoder_depth=4).cuda().eval()
+    B = 5
+    x = (torch.rand(B, 1, hw, hw, device="cuda") > 0.15).float()
+    s = torch.zeros(B, 1, hw, hw, device="cuda"); s[:, :, 0, 0] = 1
+    g = torch.zeros_like(s); g[:, :, -1, -1] = 1
+    x[:, :, 0, 0] = 1; x[:, :, -1, -1] = 1
+    with torch.no_grad():
+        learned, vanilla, (ncl, plen) = na.forward_pair(x, s, g)
+        want_l = na(x, s, g)
+        want_v = VanillaAstar().cuda()(x, s, g)
+    assert torch.equal(learned.histories, want_l.histories) and torch.equal(learned.paths, want_l.paths)
+    assert torch.equal(vanilla.histories, want_v.histories) and torch.equal(vanilla.paths, want_v.paths)
+    assert torch.equal(ncl[:B], want_l.histories.sum((1, 2, 3)).to(ncl.dtype))
+    assert torch.equal(plen[B:], want_v.paths.sum((1, 2, 3)).to(plen.dtype))

@@ -17,7 +17,7 @@ for (H, W, B) in ((32, 32, 6), (12, 12, 5), (7, 5, 3), (64, 64, 3), (40, 48, 2),
         gc = _native.backward(c, s, g, o, torch.randn_like(c), Tb, ts, 0.5)
     hist2 = _native.forward(o, s, g, o, 0.5, W * W)[0]   # aliasing path (engine 5 above 64x64)
     pair = _native.forward(c, s, g, o, 0.5, W * W, pair=True, want_counts=True)   # validation pair + counts
-    if H <= 32 and W <= 32:                               # fused encoder hand-off: logits / 9-tap products
+    if H <= 64 and W <= 64:                               # fused encoder hand-off: logits / 9-tap products
         lg = torch.randn_like(c)
         _native.forward(lg, s, g, o, 0.5, W * W, cost_kind=_native.COST_LOGIT, cost_scale=10.0)
         taps = torch.randn((B, H, W, 9), device="cuda")
