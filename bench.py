@@ -187,30 +187,58 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def _pick_threads(fn, set_threads):
-    """The host's best thread count: oversubscribing SMT siblings across sockets makes MKL-DNN / OpenMP collapse
-    (measured on the B200 host: 128 threads 10x slower than 32), so a few counts are tried and the fastest kept."""
-    ncpu = os.cpu_count() or 1
-    cands = sorted({min(ncpu, c) for c in (8, 16, 32, 64, torch.get_num_threads(), ncpu)})
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        set_threads(c)
-        fn()
+class _SweepTimeout(Exception):
+    pass
+
+
+def _bounded(fn, limit_s):
+    """Wall time of fn(), or inf when it is still running after limit_s seconds (SIGALRM raises inside the Python-level
+    loop of the reference, which executes thousands of small ops per call)."""
+    import signal
+
+    def on_alarm(signum, frame):
+        raise _SweepTimeout()
+
+    old = signal.signal(signal.SIGALRM, on_alarm)
+    signal.setitimer(signal.ITIMER_REAL, limit_s)
+    try:
         t0 = time.perf_counter()
         fn()
-        dt = time.perf_counter() - t0
+        return time.perf_counter() - t0
+    except _SweepTimeout:
+        return float("inf")
+    finally:
+        signal.setitimer(signal.ITIMER_REAL, 0.0)
+        signal.signal(signal.SIGALRM, old)
+
+
+def _pick_threads(fn, set_threads):
+    """The host's best thread count.  The reference's loop is thousands of tiny ops, each an OpenMP fork-join: past a
+    few dozen threads (and across sockets) it collapses — measured on the B200 host: 16 threads fastest, 128 unpinned
+    threads took minutes per batch.  Counts are tried in ascending order on the CPUs this process may use; every trial
+    after the first is cut off at 4x the best time so far, and the sweep stops at the first count that is slower."""
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = sorted({min(avail, c) for c in (8, 16, 32, 64, avail)})
+    best, best_t, tried = cands[0], float("inf"), []
+    for c in cands:
+        set_threads(c)
+        limit = 300.0 if best_t == float("inf") else 4.0 * best_t + 1.0
+        warm = _bounded(fn, limit)
+        dt = _bounded(fn, limit) if warm != float("inf") else float("inf")
+        tried.append(c)
         if dt < best_t:
             best, best_t = c, dt
-        if dt > 4 * best_t:
+        else:
             break
     set_threads(best)
-    return best, cands, best_t
+    return best, tried, best_t
 
 
 def bench_reference(args):
     """The reference's CPU implementation of the path on this box's host cores, rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    pinned = pin_to_gpu_numa(0)   # one socket's cores, like the GPU arm's rank 0 (cross-socket OpenMP teams are far slower)
     staged = os.path.isdir(os.path.join(REF_STAGE, "neural_astar", "planner")) and not args.port
     _paths(ours=False)
     maps, start, goal, _ = load_problem()
@@ -270,7 +298,8 @@ def bench_reference(args):
     value = m * args.steps / dt
     hist_sum = float(out.histories.sum())
     sample = (f"each step = the first {m} of the b={BATCH} maps through {what}; {threads} threads = fastest of {cands} "
-              f"on {os.cpu_count()} logical CPUs")
+              f"(ascending sweep, stopped at the first slower count) on {len(os.sched_getaffinity(0))} of "
+              f"{os.cpu_count()} logical CPUs" + (" (GPU 0's NUMA node)" if pinned else ""))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,

@@ -636,3 +636,29 @@ def test_forward_pair_with_fused_handoff(hw):
     assert torch.equal(vanilla.histories, want_v.histories) and torch.equal(vanilla.paths, want_v.paths)
     assert torch.equal(ncl[:B], want_l.histories.sum((1, 2, 3)).to(ncl.dtype))
     assert torch.equal(plen[B:], want_v.paths.sum((1, 2, 3)).to(plen.dtype))
+
+
+def test_pipelined_planner_on_64_wide_grids():
+    """PipelinedPlanner with the 64-wide engine's fused hand-off (48x48 and 64x64 planning grids)."""
+    from neural_astar.planner import NeuralAstar
+    from neural_astar.utils.inference import PipelinedPlanner
+
+    for hw in (64, 48):
+        torch.manual_seed(hw)
+        na = NeuralAstar(encoder_input="m+", encoder_arch="CNN", encoder_depth=3).cuda().eval()
+        batches = []
+        for k in range(3):
+            x = (torch.rand(6, 1, hw, hw, device="cuda") > 0.15).float()
+            s = torch.zeros(6, 1, hw, hw, device="cuda"); s[:, :, k, 0] = 1
+            g = torch.zeros_like(s); g[:, :, -1, -1 - k] = 1
+            x[:, :, k, 0] = 1; x[:, :, -1, -1 - k] = 1
+            batches.append((x, s, g))
+        with torch.no_grad():
+            want = [na(*b) for b in batches]
+        pipe = PipelinedPlanner(na, *batches[0])
+        got = [pipe.submit(*b) for b in batches]
+        got = [(o.histories.clone(), o.paths.clone()) for o in got[1:]]
+        last = pipe.drain()
+        got.append((last.histories, last.paths))
+        for (h, p), w in zip(got, want):
+            assert torch.equal(h, w.histories) and torch.equal(p, w.paths)

@@ -421,3 +421,31 @@ def test_warcraft_encoder_handoff_matches_reference():
     with torch.no_grad():
         cost = na.encode(x, torch.from_numpy(z["start"]), torch.from_numpy(z["goal"]))
     np.testing.assert_allclose(cost.numpy(), z["cost"], rtol=1e-5, atol=1e-5)
+
+
+def test_reference_arm_thread_sweep_is_bounded(monkeypatch):
+    """bench.py's reference arm picks its thread count with an ascending sweep that stops at the first slower count
+    and cuts a collapsing trial off (the PyTorch loop with 128 unpinned OpenMP threads ran for minutes per batch)."""
+    import importlib
+    import sys
+    import time
+
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(os, "sched_getaffinity", lambda _pid: set(range(128)))
+    state = {"threads": 0, "calls": []}
+    cost = {8: 0.05, 16: 0.03, 32: 0.04, 64: 0.5, 128: 5.0}
+
+    def fn():
+        state["calls"].append(state["threads"])
+        end = time.perf_counter() + cost[state["threads"]]
+        while time.perf_counter() < end:        # Python-level loop, like the reference's: the alarm can interrupt it
+            time.sleep(0.001)
+
+    best, tried, t = bench._pick_threads(fn, lambda c: state.__setitem__("threads", c))
+    assert best == 16 and tried == [8, 16, 32] and 0.02 < t < 0.2 and state["threads"] == 16
+    # a collapsing count right after the first candidate is cut off at 4x the best time + 1 s
+    cost.update({8: 0.05, 16: 60.0})
+    t0 = time.perf_counter()
+    best, tried, _ = bench._pick_threads(fn, lambda c: state.__setitem__("threads", c))
+    assert best == 8 and tried == [8, 16] and time.perf_counter() - t0 < 5.0
